@@ -1,0 +1,301 @@
+// sce_gemm.cuh — persistent, warp-specialised, batched split-bf16 GEMM on tcgen05 / TMEM / TMA.
+//
+//   D[model][i][j] = sum_set sum_k A_set[model][i,k] * B_set[model][j,k]            (fp32 in TMEM)
+//
+// with every fp32 operand carried as a (hi, lo) bf16 pair, x ~= hi + lo, and the product formed
+// as hi*hi + hi*lo + lo*hi (3 tensor-core passes, relative error ~2^-16; `passes == 1` keeps only
+// hi*hi). This is how the engine reaches the reference's true-FP32 results on the
+// bf16 tensor pipe. Operands may be K-major (reduction index contiguous in HBM) or MN-major
+// (row/column index contiguous), so no transposed copies of activations/codes are ever written.
+//
+// One CTA per SM, 256 threads: warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM
+// allocator, warps 4..7 = epilogue (TMEM -> registers -> fused epilogue -> HBM). Accumulators are
+// double-buffered in TMEM so the epilogue of tile t overlaps the main loop of tile t+1.
+#pragma once
+#include "sce_ptx.cuh"
+
+namespace sce {
+
+constexpr int kBM = 128;        // rows of the output tile == TMEM lanes
+constexpr int kGemmThreads = 256;
+constexpr int kMaxSets = 2;
+
+// What the epilogue functor sees for each tile.
+struct TileCoord {
+  int model;    // ensemble index
+  int m_blk;    // tile row index
+  int n_blk;    // tile column index
+  int row;      // global output row owned by this thread (may be >= m_total: predicate!)
+  int col0;     // first global output column of the tile
+  int warp_q;   // epilogue warp quarter 0..3 (rows 32*warp_q .. +31 of the tile)
+  int lane;
+};
+
+template <class EpiParams>
+struct GemmParams {
+  CUtensorMap a_hi[kMaxSets], a_lo[kMaxSets], b_hi[kMaxSets], b_lo[kMaxSets];
+  int a_batched[kMaxSets], b_batched[kMaxSets];  // 0: operand shared by all models
+  int nsets;      // number of (A,B) operand pairs accumulated into the same tile
+  int k_total;    // reduction length of each pair
+  int passes;     // 3: hi*hi + hi*lo + lo*hi, 1: hi*hi
+  int n_models, m_total, n_total;
+  int tiles_m, tiles_n;
+  EpiParams epi;
+};
+
+template <int BN, int BK, bool A_MN, bool B_MN, int STAGES>
+struct GemmSmem {
+  static constexpr int kATile = kBM * BK * 2;   // bytes, one of hi/lo
+  static constexpr int kBTile = BN * BK * 2;
+  static constexpr int kStage = 2 * kATile + 2 * kBTile;
+  static constexpr int kBarOff = STAGES * kStage;
+  static constexpr int kBytes = kBarOff + 256 /*barriers + tmem ptr*/ + 1024 /*align slack*/;
+};
+
+// ------------------------------------------------------------------------------------------------
+// The kernel
+// ------------------------------------------------------------------------------------------------
+template <class Epi, int BN, int BK, bool A_MN, bool B_MN, int STAGES>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_split_kernel(const __grid_constant__ GemmParams<typename Epi::Params> p) {
+  static_assert(BN % 64 == 0 && BN <= 256, "BN must be a multiple of 64, at most 256");
+  static_assert(BK % 16 == 0 && BK <= 64, "BK in {16,32,48,64}");
+  static_assert(A_MN || BK == 64, "K-major A uses one 128-byte swizzled row per tile row: BK == 64");
+  static_assert(B_MN || BK == 64, "K-major B uses one 128-byte swizzled row per tile row: BK == 64");
+  using SM = GemmSmem<BN, BK, A_MN, B_MN, STAGES>;
+  constexpr uint32_t kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
+                                 : (2 * BN <= 256) ? 256 : 512;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + SM::kBarOff);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = p.n_models * p.tiles_m * p.tiles_n;
+  const int kblocks = (p.k_total + BK - 1) / BK;
+  const bool three = p.passes >= 3;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < p.nsets; ++s) {
+      tma_prefetch_desc(&p.a_hi[s]);
+      tma_prefetch_desc(&p.b_hi[s]);
+      if (three) {
+        tma_prefetch_desc(&p.a_lo[s]);
+        tma_prefetch_desc(&p.b_lo[s]);
+      }
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_ptr, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ======================= TMA producer =======================
+    if (lane == 0) {
+      const uint32_t stage_bytes = three ? uint32_t(SM::kStage) : uint32_t(SM::kATile + SM::kBTile);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int model = tile / (p.tiles_m * p.tiles_n);
+        const int rem = tile - model * (p.tiles_m * p.tiles_n);
+        const int m_blk = rem / p.tiles_n;
+        const int n_blk = rem - m_blk * p.tiles_n;
+        for (int set = 0; set < p.nsets; ++set) {
+          const int am = p.a_batched[set] ? model : 0;
+          const int bm = p.b_batched[set] ? model : 0;
+          for (int kb = 0; kb < kblocks; ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sa_hi = smem + stage * SM::kStage;
+            uint8_t* sa_lo = sa_hi + SM::kATile;
+            uint8_t* sb_hi = sa_lo + SM::kATile;
+            uint8_t* sb_lo = sb_hi + SM::kBTile;
+            mbar_expect_tx(&full_bar[stage], stage_bytes);
+            const int k0 = kb * BK;
+            if constexpr (!A_MN) {
+              tma_load_3d(sa_hi, &p.a_hi[set], &full_bar[stage], k0, m_blk * kBM, am);
+              if (three) tma_load_3d(sa_lo, &p.a_lo[set], &full_bar[stage], k0, m_blk * kBM, am);
+            } else {
+#pragma unroll
+              for (int j = 0; j < kBM / 64; ++j) {
+                tma_load_3d(sa_hi + j * (BK * 128), &p.a_hi[set], &full_bar[stage],
+                            m_blk * kBM + j * 64, k0, am);
+                if (three)
+                  tma_load_3d(sa_lo + j * (BK * 128), &p.a_lo[set], &full_bar[stage],
+                              m_blk * kBM + j * 64, k0, am);
+              }
+            }
+            if constexpr (!B_MN) {
+              tma_load_3d(sb_hi, &p.b_hi[set], &full_bar[stage], k0, n_blk * BN, bm);
+              if (three) tma_load_3d(sb_lo, &p.b_lo[set], &full_bar[stage], k0, n_blk * BN, bm);
+            } else {
+#pragma unroll
+              for (int j = 0; j < BN / 64; ++j) {
+                tma_load_3d(sb_hi + j * (BK * 128), &p.b_hi[set], &full_bar[stage],
+                            n_blk * BN + j * 64, k0, bm);
+                if (three)
+                  tma_load_3d(sb_lo + j * (BK * 128), &p.b_lo[set], &full_bar[stage],
+                              n_blk * BN + j * 64, k0, bm);
+              }
+            }
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ======================= MMA issuer =======================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(kBM, BN, A_MN, B_MN);
+      constexpr uint32_t a_lbo = A_MN ? BK * 128 : 16;
+      constexpr uint32_t b_lbo = B_MN ? BK * 128 : 16;
+      constexpr uint32_t a_kstep = A_MN ? 2048 : 32;  // bytes per K=16 slice
+      constexpr uint32_t b_kstep = B_MN ? 2048 : 32;
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + uint32_t(acc * BN);
+        uint32_t accumulate = 0;
+        for (int it = 0; it < p.nsets * kblocks; ++it) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa_hi = smem_u32(smem + stage * SM::kStage);
+          const uint32_t sa_lo = sa_hi + SM::kATile;
+          const uint32_t sb_hi = sa_lo + SM::kATile;
+          const uint32_t sb_lo = sb_hi + SM::kBTile;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t ah = make_sdesc_sw128(sa_hi + k * a_kstep, a_lbo, 1024);
+            const uint64_t bh = make_sdesc_sw128(sb_hi + k * b_kstep, b_lbo, 1024);
+            if (three) {
+              const uint64_t al = make_sdesc_sw128(sa_lo + k * a_kstep, a_lbo, 1024);
+              const uint64_t bl = make_sdesc_sw128(sb_lo + k * b_kstep, b_lbo, 1024);
+              // small cross terms first, then the dominant hi*hi term
+              umma_bf16(d_tmem, al, bh, idesc, accumulate);
+              umma_bf16(d_tmem, ah, bl, idesc, 1);
+              umma_bf16(d_tmem, ah, bh, idesc, 1);
+            } else {
+              umma_bf16(d_tmem, ah, bh, idesc, accumulate);
+            }
+            accumulate = 1;
+          }
+          umma_commit(&empty_bar[stage]);  // smem slot is free once these MMAs have read it
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ======================= epilogue =======================
+    const int wq = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      TileCoord tc;
+      tc.model = tile / (p.tiles_m * p.tiles_n);
+      const int rem = tile - tc.model * (p.tiles_m * p.tiles_n);
+      tc.m_blk = rem / p.tiles_n;
+      tc.n_blk = rem - tc.m_blk * p.tiles_n;
+      tc.row = tc.m_blk * kBM + wq * 32 + lane;
+      tc.col0 = tc.n_blk * BN;
+      tc.warp_q = wq;
+      tc.lane = lane;
+      Epi epi(p.epi, tc, p.m_total, p.n_total);
+
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + uint32_t(acc * BN) + (uint32_t(wq * 32) << 16);
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld32(taddr + uint32_t(c * 32), r);
+        tmem_ld_wait();
+        if (c == BN / 32 - 1) {
+          // all TMEM reads of this accumulator are done: hand it back to the MMA warp early
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        }
+        epi.chunk(c * 32, r);
+      }
+      epi.finish();
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Epilogue: plain fp32 store  out[model][row][col] = acc   (dW tiles; self-test)
+// ------------------------------------------------------------------------------------------------
+struct EpiStoreF32 {
+  struct Params {
+    float* out;
+    long long model_stride;  // elements
+    int ld;                  // elements
+  };
+  const Params& P;
+  const TileCoord& T;
+  int m_total, n_total;
+  __device__ EpiStoreF32(const Params& p, const TileCoord& t, int m, int n)
+      : P(p), T(t), m_total(m), n_total(n) {}
+  __device__ __forceinline__ void chunk(int c, const uint32_t (&r)[32]) {
+    if (T.row >= m_total) return;
+    float* o = P.out + (long long)T.model * P.model_stride + (long long)T.row * P.ld + T.col0 + c;
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      if (T.col0 + c + j < n_total) {  // n_total % 4 == 0 is required by the host
+        float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                               __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+        *reinterpret_cast<float4*>(o + j) = v;
+      }
+    }
+  }
+  __device__ __forceinline__ void finish() {}
+};
+
+}  // namespace sce

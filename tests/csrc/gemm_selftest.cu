@@ -1,0 +1,261 @@
+// gemm_selftest.cu — standalone check of the tcgen05 split-bf16 GEMM core (sce_gemm.cuh) against
+// a double-precision CPU product, for every operand-major / tile / pass configuration the engine
+// instantiates. Build: see Makefile target `selftest`. Runs on one B200; exits non-zero on failure.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../../sparse_coding_b200/csrc/sce_gemm.cuh"
+#include "../../sparse_coding_b200/csrc/sce_tmap.h"
+
+using namespace sce;
+
+#define CK(x)                                                                    \
+  do {                                                                           \
+    cudaError_t e_ = (x);                                                        \
+    if (e_ != cudaSuccess) {                                                     \
+      printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); \
+      exit(2);                                                                   \
+    }                                                                            \
+  } while (0)
+
+static uint32_t rng_state = 12345u;
+static float frand() {  // uniform in [-1, 1)
+  rng_state = rng_state * 1664525u + 1013904223u;
+  return (float)((rng_state >> 8) & 0xFFFFFF) / 8388608.0f - 1.0f;
+}
+
+struct Split {
+  std::vector<__nv_bfloat16> hi, lo;
+  __nv_bfloat16 *d_hi = nullptr, *d_lo = nullptr;
+};
+
+static void split_upload(const std::vector<float>& x, Split& s) {
+  s.hi.resize(x.size());
+  s.lo.resize(x.size());
+  for (size_t i = 0; i < x.size(); ++i) {
+    s.hi[i] = __float2bfloat16_rn(x[i]);
+    s.lo[i] = __float2bfloat16_rn(x[i] - __bfloat162float(s.hi[i]));
+  }
+  CK(cudaMalloc(&s.d_hi, x.size() * 2));
+  CK(cudaMalloc(&s.d_lo, x.size() * 2));
+  CK(cudaMemcpy(s.d_hi, s.hi.data(), x.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(s.d_lo, s.lo.data(), x.size() * 2, cudaMemcpyHostToDevice));
+}
+static void split_free(Split& s) {
+  cudaFree(s.d_hi);
+  cudaFree(s.d_lo);
+}
+
+// One logical operand: [models][rows][K] if K-major, [models][K][rows] if MN-major.
+struct Operand {
+  int models, rows, K;
+  bool mn;
+  std::vector<float> x;
+  Split s;
+  float at(int m, int r, int k) const {
+    return mn ? x[((size_t)m * K + k) * rows + r] : x[((size_t)m * rows + r) * K + k];
+  }
+  float hi(int m, int r, int k) const {
+    size_t i = mn ? ((size_t)m * K + k) * rows + r : ((size_t)m * rows + r) * K + k;
+    return __bfloat162float(s.hi[i]);
+  }
+  float lo(int m, int r, int k) const {
+    size_t i = mn ? ((size_t)m * K + k) * rows + r : ((size_t)m * rows + r) * K + k;
+    return __bfloat162float(s.lo[i]);
+  }
+};
+
+static void make_operand(Operand& o, int models, int rows, int K, bool mn) {
+  o.models = models;
+  o.rows = rows;
+  o.K = K;
+  o.mn = mn;
+  o.x.resize((size_t)models * rows * K);
+  for (auto& v : o.x) v = frand();
+  split_upload(o.x, o.s);
+}
+
+static bool tmaps(const Operand& o, uint32_t box_rows_kmajor, int BK, CUtensorMap* hi,
+                  CUtensorMap* lo) {
+  if (!o.mn) {
+    return make_tmap_bf16(hi, o.s.d_hi, o.models, o.rows, o.K, o.K, (uint64_t)o.rows * o.K,
+                          box_rows_kmajor) &&
+           make_tmap_bf16(lo, o.s.d_lo, o.models, o.rows, o.K, o.K, (uint64_t)o.rows * o.K,
+                          box_rows_kmajor);
+  }
+  return make_tmap_bf16(hi, o.s.d_hi, o.models, o.K, o.rows, o.rows, (uint64_t)o.rows * o.K, BK) &&
+         make_tmap_bf16(lo, o.s.d_lo, o.models, o.K, o.rows, o.rows, (uint64_t)o.rows * o.K, BK);
+}
+
+template <int BN, int BK, bool A_MN, bool B_MN, int STAGES>
+static bool run_case(const char* name, int models, int M, int N, int K, int nsets, int passes,
+                     bool a_shared, bool b_shared) {
+  Operand A[2], B[2];
+  for (int s = 0; s < nsets; ++s) {
+    make_operand(A[s], a_shared ? 1 : models, M, K, A_MN);
+    make_operand(B[s], b_shared ? 1 : models, N, K, B_MN);
+  }
+  float* d_out;
+  size_t out_elems = (size_t)models * M * N;
+  CK(cudaMalloc(&d_out, out_elems * 4));
+  CK(cudaMemset(d_out, 0xFF, out_elems * 4));  // NaN pattern: unwritten outputs are caught
+
+  GemmParams<EpiStoreF32::Params> p;
+  memset(&p, 0, sizeof(p));
+  for (int s = 0; s < nsets; ++s) {
+    if (!tmaps(A[s], kBM, BK, &p.a_hi[s], &p.a_lo[s]) || !tmaps(B[s], BN, BK, &p.b_hi[s], &p.b_lo[s])) {
+      printf("[%s] tensor map encode failed\n", name);
+      return false;
+    }
+    p.a_batched[s] = a_shared ? 0 : 1;
+    p.b_batched[s] = b_shared ? 0 : 1;
+  }
+  p.nsets = nsets;
+  p.k_total = K;
+  p.passes = passes;
+  p.n_models = models;
+  p.m_total = M;
+  p.n_total = N;
+  p.tiles_m = (M + kBM - 1) / kBM;
+  p.tiles_n = (N + BN - 1) / BN;
+  p.epi.out = d_out;
+  p.epi.model_stride = (long long)M * N;
+  p.epi.ld = N;
+
+  using SM = GemmSmem<BN, BK, A_MN, B_MN, STAGES>;
+  auto kern = gemm_split_kernel<EpiStoreF32, BN, BK, A_MN, B_MN, STAGES>;
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kBytes));
+  int sms = 0;
+  CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
+  int tiles = models * p.tiles_m * p.tiles_n;
+  int grid = tiles < sms ? tiles : sms;
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  CK(cudaEventRecord(e0));
+  kern<<<grid, kGemmThreads, SM::kBytes>>>(p);
+  CK(cudaEventRecord(e1));
+  cudaError_t err = cudaDeviceSynchronize();
+  if (err != cudaSuccess) {
+    printf("[%s] kernel failed: %s\n", name, cudaGetErrorString(err));
+    exit(3);  // context is dead after a device fault
+  }
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, e0, e1));
+
+  std::vector<float> out(out_elems);
+  CK(cudaMemcpy(out.data(), d_out, out_elems * 4, cudaMemcpyDeviceToHost));
+
+  // Reference in double. `exact` uses the same (hi, lo) decomposition the device used so the only
+  // differences are fp32 accumulation order; `full` is the true fp32-input product.
+  double max_err_exact = 0, max_err_full = 0, max_ref = 0;
+  long long bad = 0;
+  int first_bad[3] = {-1, -1, -1};
+  // sample rows/cols to keep the CPU check fast for big cases
+  int rstep = M > 512 ? 37 : 1, cstep = N > 512 ? 29 : 1;
+  for (int m = 0; m < models; ++m)
+    for (int i = 0; i < M; i += rstep)
+      for (int j = 0; j < N; j += cstep) {
+        double ex = 0, fu = 0;
+        for (int s = 0; s < nsets; ++s) {
+          const int am = a_shared ? 0 : m, bm = b_shared ? 0 : m;
+          for (int k = 0; k < K; ++k) {
+            double ah = A[s].hi(am, i, k), al = A[s].lo(am, i, k);
+            double bh = B[s].hi(bm, j, k), bl = B[s].lo(bm, j, k);
+            ex += passes >= 3 ? (ah * bh + ah * bl + al * bh) : ah * bh;
+            fu += (double)A[s].at(am, i, k) * (double)B[s].at(bm, j, k);
+          }
+        }
+        double got = out[((size_t)m * M + i) * N + j];
+        double ee = fabs(got - ex), ef = fabs(got - fu);
+        if (!(ee == ee)) ee = 1e30;  // NaN
+        if (ee > max_err_exact) max_err_exact = ee;
+        if (ef == ef && ef > max_err_full) max_err_full = ef;
+        if (fabs(ex) > max_ref) max_ref = fabs(ex);
+        if (ee > 1e-3 * sqrt((double)K * nsets)) {
+          if (!bad) {
+            first_bad[0] = m;
+            first_bad[1] = i;
+            first_bad[2] = j;
+          }
+          ++bad;
+        }
+      }
+  double flops = 2.0 * models * M * N * (double)K * nsets * (passes >= 3 ? 3 : 1);
+  bool ok = bad == 0;
+  printf("[%s] %s  models=%d M=%d N=%d K=%d sets=%d passes=%d  max|err| vs split-exact %.3e, vs fp32 "
+         "product %.3e (max|ref| %.2f)  %.3f ms  %.1f TF(bf16-pass)\n",
+         name, ok ? "PASS" : "FAIL", models, M, N, K, nsets, passes, max_err_exact, max_err_full,
+         max_ref, ms, flops / ms * 1e-9);
+  if (!ok) {
+    printf("    %lld bad samples; first at model %d row %d col %d: got %.6f\n", bad, first_bad[0],
+           first_bad[1], first_bad[2],
+           out[((size_t)first_bad[0] * M + first_bad[1]) * N + first_bad[2]]);
+    // error map by 8-row / 64-col blocks of model 0 to expose layout mistakes
+    int m = first_bad[0];
+    for (int i = 0; i < (M < 32 ? M : 32); i += 4) {
+      printf("    row %3d:", i);
+      for (int j = 0; j < (N < 256 ? N : 256); j += 16) {
+        double ex = 0;
+        for (int s = 0; s < nsets; ++s)
+          for (int k = 0; k < K; ++k) {
+            const int am = a_shared ? 0 : m, bm = b_shared ? 0 : m;
+            double ah = A[s].hi(am, i, k), al = A[s].lo(am, i, k);
+            double bh = B[s].hi(bm, j, k), bl = B[s].lo(bm, j, k);
+            ex += passes >= 3 ? (ah * bh + ah * bl + al * bh) : ah * bh;
+          }
+        double got = out[((size_t)m * M + i) * N + j];
+        printf(" %c", fabs(got - ex) < 1e-3 * sqrt((double)K * nsets) ? '.' : 'X');
+      }
+      printf("\n");
+    }
+  }
+  for (int s = 0; s < nsets; ++s) {
+    split_free(A[s].s);
+    split_free(B[s].s);
+  }
+  cudaFree(d_out);
+  return ok;
+}
+
+int main(int argc, char** argv) {
+  bool big = argc > 1 && !strcmp(argv[1], "--big");
+  int dev = 0;
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, dev));
+  printf("device: %s  sm_%d%d  SMs=%d\n", prop.name, prop.major, prop.minor,
+         prop.multiProcessorCount);
+  bool ok = true;
+  // ---- K-major x K-major (encode / dC shape), increasing complexity
+  ok &= run_case<256, 64, false, false, 2>("kk_k16", 1, 128, 256, 16, 1, 1, false, false);
+  ok &= run_case<256, 64, false, false, 2>("kk_k64", 1, 128, 256, 64, 1, 1, false, false);
+  ok &= run_case<256, 64, false, false, 2>("kk_k256", 1, 128, 256, 256, 1, 1, false, false);
+  ok &= run_case<256, 64, false, false, 2>("kk_3pass", 1, 128, 256, 256, 1, 3, false, false);
+  ok &= run_case<256, 64, false, false, 2>("kk_multi", 3, 384, 512, 512, 1, 3, true, false);
+  ok &= run_case<256, 64, false, false, 2>("kk_ragged", 2, 200, 328, 104, 1, 3, true, false);
+  ok &= run_case<128, 64, false, false, 3>("kk_bn128", 2, 256, 384, 256, 1, 3, true, false);
+  // ---- K-major A x MN-major B (decode shape: X^ = C W)
+  ok &= run_case<256, 64, false, true, 2>("kmn_k16", 1, 128, 256, 16, 1, 1, false, false);
+  ok &= run_case<256, 64, false, true, 2>("kmn_k64", 1, 128, 256, 64, 1, 1, false, false);
+  ok &= run_case<256, 64, false, true, 2>("kmn_3pass", 2, 256, 512, 512, 1, 3, false, false);
+  ok &= run_case<256, 64, false, true, 2>("kmn_ragged", 2, 200, 328, 104, 1, 3, false, false);
+  // ---- MN-major x MN-major (weight-gradient shape: dW = dZ^T X + C^T G), two operand sets
+  ok &= run_case<256, 64, true, true, 2>("mnmn_k16", 1, 128, 256, 16, 1, 1, false, false);
+  ok &= run_case<256, 64, true, true, 2>("mnmn_k64", 1, 128, 256, 64, 1, 1, false, false);
+  ok &= run_case<256, 64, true, true, 2>("mnmn_2set", 2, 256, 512, 320, 2, 3, false, true);
+  ok &= run_case<256, 32, true, true, 4>("mnmn_bk32", 2, 256, 512, 320, 2, 3, false, true);
+  ok &= run_case<256, 32, true, true, 4>("mnmn_ragged", 2, 200, 328, 104, 2, 3, false, true);
+  if (big) {
+    // config-2 shapes, one model's worth of each GEMM, for a first throughput reading
+    ok &= run_case<256, 64, false, false, 2>("big_encode", 4, 8192, 4096, 512, 1, 3, true, false);
+    ok &= run_case<256, 64, false, true, 2>("big_decode", 4, 8192, 512, 4096, 1, 3, false, false);
+    ok &= run_case<256, 32, true, true, 4>("big_dw", 4, 4096, 512, 8192, 2, 3, false, true);
+    ok &= run_case<256, 64, true, true, 2>("big_dw64", 4, 4096, 512, 8192, 2, 3, false, true);
+    ok &= run_case<256, 64, false, false, 2>("big_enc1p", 4, 8192, 4096, 512, 1, 1, true, false);
+  }
+  printf(ok ? "ALL PASS\n" : "SOME FAILED\n");
+  return ok ? 0 : 1;
+}
