@@ -1,0 +1,145 @@
+/* sce.h — C ABI of the B200-native ensemble sparse-autoencoder training engine (libsce.so).
+ *
+ * The reference (HoagyC/sparse_coding @ 69c5ae0) has no FFI layer: its boundary for this path is the Python
+ * protocol DictSignature / FunctionalEnsemble (autoencoders/ensemble.py:15-22, 68-193). This library sits
+ * UNDERNEATH that protocol: sparse_coding_b200.FunctionalEnsemble keeps the reference's Python surface and
+ * forwards the arithmetic of `step_batch` to the entry points below through ctypes (see INTEGRATION.md for the
+ * binding a maintainer of the reference would add).
+ *
+ * Conventions: plain pointers and sizes only (no torch types); device pointers are borrowed — the caller (torch)
+ * owns parameters, optimiser moments and the workspace, which are updated IN PLACE exactly as
+ * FunctionalEnsemble.step_batch does (ensemble.py:182-191); no device allocation and no C++ exception crosses
+ * the ABI; every call returns 0 on success or a negative sce_status, with a thread-local message available from
+ * sce_last_error(); work is enqueued asynchronously on the caller's CUDA stream (`stream` is a cudaStream_t
+ * passed as void*); calls on different plans are re-entrant, calls on the same plan are not thread-safe.
+ */
+#ifndef SCE_H_
+#define SCE_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SCE_VERSION 100 /* major*10000 + minor*100 + patch */
+
+typedef enum sce_status {
+  SCE_OK = 0,
+  SCE_ERR_INVALID = -1,    /* bad argument / unsupported shape */
+  SCE_ERR_CUDA = -2,       /* a CUDA runtime or driver call failed */
+  SCE_ERR_WORKSPACE = -3,  /* workspace too small / misaligned */
+  SCE_ERR_NO_DEVICE = -4   /* no sm_100 device / driver entry point missing */
+} sce_status;
+
+/* Which reference signature the plan reproduces. */
+typedef enum sce_variant {
+  SCE_TIED = 0,   /* FunctionalTiedSAE.loss   (sae_ensemble.py:135-162); + coef_mask = FunctionalMaskedTiedSAE (:347-373) */
+  SCE_UNTIED = 1, /* FunctionalSAE.loss       (sae_ensemble.py:53-78);   + coef_mask = FunctionalMaskedSAE     (:418-444) */
+  SCE_TOPK = 2    /* TopKEncoder.loss         (topk_encoder.py:29-40) */
+} sce_variant;
+
+/* How the Adam step counter behaves. */
+typedef enum sce_adam_count {
+  SCE_ADAM_FROZEN_T1 = 0, /* the reference: step_batch drops torchopt's incremented count (ensemble.py:185-189) */
+  SCE_ADAM_STANDARD = 1   /* bias correction with the true step number */
+} sce_adam_count;
+
+/* Static description of one stacked ensemble (FunctionalEnsemble.__init__, ensemble.py:69-97). */
+typedef struct sce_desc {
+  int variant;          /* sce_variant */
+  int n_models;         /* M: models stacked on dim 0 */
+  int d;                /* activation width, multiple of 8 */
+  int n;                /* dictionary rows (stack size for masked variants), multiple of 8 */
+  int batch_max;        /* largest batch this plan will see (the last batch of a chunk may be shorter, Q7) */
+  int x_per_model;      /* 0: one [B,d] batch shared by all models (expand_dims=True); 1: [M,B,d] */
+  float lr, beta1, beta2, eps, eps_root; /* torchopt.adam hyper-parameters */
+  int adam_count_mode;  /* sce_adam_count */
+  int fwd_passes;       /* 3: split-bf16 (hi*hi+hi*lo+lo*hi, ~fp32 accuracy; default), 1: plain bf16 */
+  int bwd_passes;       /* same for the three backward GEMMs */
+  float norm_floor;     /* clamp floor of the row norms: 1e-8 (SAE variants); <= 0 disables it (TopK) */
+} sce_desc;
+
+/* Device pointers owned by the caller; all fp32 unless noted. Unused ones are NULL. */
+typedef struct sce_buffers {
+  float* encoder;       /* [M,n,d]  params["encoder"] (tied/untied) or params["dict"] (topk) */
+  float* encoder_bias;  /* [M,n]    params["encoder_bias"]; NULL for topk */
+  float* decoder;       /* [M,n,d]  params["decoder"]; untied only */
+  float* encoder_m;     /* Adam first moment of encoder, same shape; likewise below */
+  float* encoder_v;
+  float* bias_m;
+  float* bias_v;
+  float* decoder_m;
+  float* decoder_v;
+  const float* l1_alpha;          /* [M]   buffers["l1_alpha"]; NULL = 0 (topk) */
+  const float* bias_decay;        /* [M]   buffers["bias_decay"]; NULL = 0 */
+  const unsigned char* coef_mask; /* [M,n] buffers["coef_mask"] (1 = unused coefficient) or NULL */
+  const long long* sparsity;      /* [M]   buffers["sparsity"] (topk k) or NULL */
+  void* workspace;                /* >= sce_workspace_bytes(desc), 1024-byte aligned */
+  size_t workspace_bytes;
+} sce_buffers;
+
+typedef struct sce_plan sce_plan;
+
+/* Loss columns written by sce_step: out_losses[m*SCE_LOSS_COLS + k]. */
+enum { SCE_LOSS_TOTAL = 0, SCE_LOSS_RECONSTRUCTION = 1, SCE_LOSS_L1 = 2, SCE_LOSS_BIAS_DECAY = 3, SCE_LOSS_COLS = 4 };
+
+int sce_version(void);
+const char* sce_last_error(void);
+
+/* Bytes of device scratch a plan needs (bf16 hi/lo operand copies of the dictionary, the batch, the code, the
+ * residual and the code gradient; fp32 weight gradients; reduction partials). */
+size_t sce_workspace_bytes(const sce_desc* desc);
+
+/* Builds the TMA descriptors and kernel launch plan. Does not touch device memory. */
+int sce_plan_create(const sce_desc* desc, const sce_buffers* buffers, sce_plan** out_plan);
+int sce_plan_destroy(sce_plan* plan);
+
+/* (Re)derive the normalised bf16 hi/lo operand copies of the dictionaries from the fp32 parameters. Must be
+ * called once before the first step and again whenever the caller modified the parameters itself. */
+int sce_prepare(sce_plan* plan, void* stream);
+
+/* One optimisation step for all M models on one batch == FunctionalEnsemble.step_batch (ensemble.py:175-193):
+ * forward, losses, backward, Adam, in-place parameter update.
+ *   x          device fp32, [B,d] (x_per_model = 0) or [M,B,d]
+ *   out_losses device fp32 [M, SCE_LOSS_COLS]
+ *   out_nnz    device fp32 [M]: mean over the batch of count_nonzero(c, -1)  (big_sweep.py:171)            */
+int sce_step(sce_plan* plan, const float* x, int B, float* out_losses, float* out_nnz, void* stream);
+
+/* Same step, fed from HOST memory the way the reference loop feeds it (big_sweep.py:168): copies `x_host`
+ * (pinned or pageable fp32) to the device, steps, copies the [M,SCE_LOSS_COLS] losses and [M] nnz back, and
+ * synchronises the stream before returning. */
+int sce_step_host(sce_plan* plan, const float* x_host, int B, float* out_losses_host, float* out_nnz_host,
+                  void* stream);
+
+/* Forward only (evaluation; LearnedDict.predict semantics on already-centred inputs): writes x_hat
+ * [M,B,d] fp32 if non-NULL and the same losses / nnz as sce_step, without touching parameters. */
+int sce_forward(sce_plan* plan, const float* x, int B, float* x_hat, float* out_losses, float* out_nnz,
+                void* stream);
+
+/* Materialise the fp32 code tensor aux["c"] [M,B,n] of the most recent step/forward (compat path for callers
+ * that really want the dense tensor the reference returns, ensemble.py:193). */
+int sce_read_code(sce_plan* plan, int B, float* out_code, void* stream);
+
+/* Materialise the fp32 parameter gradients of the most recent sce_grads call (parity tests). */
+int sce_grads(sce_plan* plan, const float* x, int B, float* d_encoder, float* d_bias, float* d_decoder,
+              float* out_losses, float* out_nnz, void* stream);
+
+/* Split a row-gathered, optionally mean-centred batch out of a resident activation chunk:
+ *   out[r,:] = float(chunk[idx[r],:]) - sub[:]      chunk fp16 or fp32 [N,d]; idx int64 [B] or NULL (identity)
+ * (big_sweep.py:168 `dataset[batch_idxs]`, :359-364 centring) */
+int sce_gather_rows(const void* chunk, int chunk_is_half, long long n_rows, int d, const long long* idx, int B,
+                    const float* sub, float* out, void* stream);
+
+/* Optimiser step counter (number of sce_step calls so far); settable so a resumed run keeps the bias correction
+ * of SCE_ADAM_STANDARD continuous. */
+long long sce_get_step_count(const sce_plan* plan);
+int sce_set_step_count(sce_plan* plan, long long steps_taken);
+
+/* Number of kernels the most recent sce_step / sce_forward on this plan launched. */
+int sce_last_launch_count(const sce_plan* plan);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCE_H_ */

@@ -124,12 +124,16 @@ def _bias_decay_grad(b, bias_decay):
     return bias_decay * b / nb
 
 
-def tied_grads(E, b, X, alpha, bias_decay=0.0, coef_mask=None) -> Dict[str, Tensor]:
+def tied_grads(E, b, X, alpha, bias_decay=0.0, coef_mask=None, active=None) -> Dict[str, Tensor]:
+    """``active`` (bool [B, n], optional) overrides the ReLU activity pattern [z > 0]: the loss is discontinuous in
+    its derivative where a pre-activation is within rounding of zero, so a checker comparing two precisions must
+    be able to pin the pattern for those (measure-zero) coefficients."""
     f = tied_forward(E, b, X, alpha, bias_decay, coef_mask)
     B, d = X.shape
     G = 2.0 * (f["x_hat"] - X) / (B * d)                       # dL/dx_hat
-    dC = G @ f["W"].T + (alpha / B) * (f["c"] > 0).to(X.dtype)  # sign(0) = 0 for the L1 term
-    gate = f["Z"] >= 0                                          # clamp(min=0) passes gradient at exactly 0
+    pos = (f["c"] > 0) if active is None else active
+    dC = G @ f["W"].T + (alpha / B) * pos.to(X.dtype)           # sign(0) = 0 for the L1 term
+    gate = (f["Z"] >= 0) if active is None else (active | (f["Z"] == 0))  # clamp passes gradient at exactly 0
     if coef_mask is not None:
         gate = gate & ~coef_mask
     dZ = dC * gate.to(X.dtype)

@@ -1,0 +1,668 @@
+// sce_engine.cu — libsce.so: the C ABI of include/sce.h on top of the tcgen05 GEMM core and the
+// streaming kernels. One `sce_plan` = one stacked ensemble (FunctionalEnsemble, autoencoders/ensemble.py:68-97).
+//
+// One training step (tied variant; untied and top-k differ as noted) is
+//   split_rows      x -> (x_hi, x_lo)
+//   GEMM encode     z = x W^T (+b) -> relu -> (c_hi, c_lo), sum|c|, nnz          [M x B x n, K = d]
+//   GEMM decode     x^ = c W -> r = x^ - x, sum r^2, g = 2r/(Bd) -> (g_hi, g_lo)  [M x B x d, K = n]
+//   GEMM dcode      dz = (g W^T + alpha/B [c>0]) [z>=0] -> (dz_hi, dz_lo), db partials
+//   GEMM dW         dW = dz^T x + c^T g                                            [M x n x d, K = 2B]
+//   bias_norm, finalize (losses), dict_rows<ADAM> (Jacobian + Adam + renormalise + re-split), bias<ADAM>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <new>
+
+#include "../../include/sce.h"
+#include "sce_epilogues.cuh"
+#include "sce_gemm.cuh"
+#include "sce_kernels.cuh"
+#include "sce_tmap.h"
+
+using namespace sce;
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define CUDA_TRY(x)                                                                            \
+  do {                                                                                         \
+    cudaError_t e_ = (x);                                                                      \
+    if (e_ != cudaSuccess) return fail(SCE_ERR_CUDA, "%s failed: %s", #x, cudaGetErrorString(e_)); \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// plan
+// ------------------------------------------------------------------------------------------------
+struct GemmMaps {  // tensor maps of one GEMM for one batch size
+  CUtensorMap a_hi[kMaxSets], a_lo[kMaxSets], b_hi[kMaxSets], b_lo[kMaxSets];
+};
+struct BatchMaps {
+  GemmMaps encode, decode, dcode, dw_enc, dw_dec;
+};
+
+struct sce_plan {
+  sce_desc d;
+  sce_buffers b;
+  int sms;
+  int xm;  // number of distinct input batches (1 shared, or M)
+  // workspace carve-up
+  float* x_stage;                 // [xm, Bmax, d] staging for host-fed steps
+  __nv_bfloat16 *x_hi, *x_lo;     // [xm, Bmax, d]
+  __nv_bfloat16 *wenc_hi, *wenc_lo, *wdec_hi, *wdec_lo;  // [M, n, d] (tied: dec aliases enc)
+  __nv_bfloat16 *c_hi, *c_lo;     // [M, Bmax, n]
+  __nv_bfloat16 *g_hi, *g_lo;     // [M, Bmax, d]
+  __nv_bfloat16 *dz_hi, *dz_lo;   // [M, Bmax, n]   (top-k: fp32 scores alias this pair)
+  float *dw_enc, *dw_dec;         // [M, n, d]
+  float *part_enc, *part_dec, *db_part, *bnorm, *l1_over_b, *loss_stage, *nnz_stage;
+  int tiles_mB_max;
+  std::map<int, BatchMaps*>* maps;
+  int last_launches;
+  long long step;  // number of optimiser steps taken
+};
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct Carve {
+  uint8_t* base;
+  size_t off;
+  template <class T>
+  T* take(size_t count) {
+    off = align_up(off, 1024);
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += count * sizeof(T);
+    return p;
+  }
+};
+
+static int validate(const sce_desc* d) {
+  if (!d) return fail(SCE_ERR_INVALID, "desc is NULL");
+  if (d->variant < SCE_TIED || d->variant > SCE_TOPK) return fail(SCE_ERR_INVALID, "unknown variant %d", d->variant);
+  if (d->n_models < 1 || d->batch_max < 1) return fail(SCE_ERR_INVALID, "n_models and batch_max must be >= 1");
+  if (d->d < 8 || d->d % 8 || d->n < 8 || d->n % 8)
+    return fail(SCE_ERR_INVALID, "d (%d) and n (%d) must be positive multiples of 8", d->d, d->n);
+  if (d->d > 2048) return fail(SCE_ERR_INVALID, "d = %d > 2048 is not supported by the row kernels", d->d);
+  if ((d->fwd_passes != 1 && d->fwd_passes != 3) || (d->bwd_passes != 1 && d->bwd_passes != 3))
+    return fail(SCE_ERR_INVALID, "fwd_passes / bwd_passes must be 1 or 3");
+  return SCE_OK;
+}
+
+// Carves the workspace; with base == nullptr only measures it.
+static size_t carve(sce_plan* p, const sce_desc& d, uint8_t* base) {
+  Carve c{base, 0};
+  const size_t M = d.n_models, B = d.batch_max, n = d.n, dd = d.d;
+  const size_t xm = d.x_per_model ? M : 1;
+  const size_t tiles_mB = (B + kBM - 1) / kBM;
+  const size_t tiles_nN = (n + 127) / 128;  // upper bound over the BN choices (BN >= 128)
+  const size_t tiles_nD = (dd + 127) / 128;
+  auto X = c.take<float>(xm * B * dd);
+  auto xh = c.take<__nv_bfloat16>(xm * B * dd);
+  auto xl = c.take<__nv_bfloat16>(xm * B * dd);
+  auto weh = c.take<__nv_bfloat16>(M * n * dd);
+  auto wel = c.take<__nv_bfloat16>(M * n * dd);
+  __nv_bfloat16 *wdh = weh, *wdl = wel;
+  if (d.variant == SCE_UNTIED) {
+    wdh = c.take<__nv_bfloat16>(M * n * dd);
+    wdl = c.take<__nv_bfloat16>(M * n * dd);
+  }
+  auto ch = c.take<__nv_bfloat16>(M * B * n);
+  auto cl = c.take<__nv_bfloat16>(M * B * n);
+  auto gh = c.take<__nv_bfloat16>(M * B * dd);
+  auto gl = c.take<__nv_bfloat16>(M * B * dd);
+  auto dzh = c.take<__nv_bfloat16>(2 * M * B * n);  // hi then lo, contiguous: 4 B / element in total
+  auto dwe = c.take<float>(M * n * dd);
+  float* dwd = dwe;
+  if (d.variant == SCE_UNTIED) dwd = c.take<float>(M * n * dd);
+  const size_t enc_parts = d.variant == SCE_TOPK ? B : tiles_mB * 4 * tiles_nN;
+  auto pe = c.take<float>(M * enc_parts * 2);
+  auto pd = c.take<float>(M * tiles_mB * 4 * tiles_nD);
+  auto dbp = c.take<float>(M * tiles_mB * 4 * n);
+  auto bn = c.take<float>(M);
+  auto lob = c.take<float>(M);
+  auto ls = c.take<float>(M * 4);
+  auto ns = c.take<float>(M);
+  if (p) {
+    p->x_stage = X;
+    p->x_hi = xh;
+    p->x_lo = xl;
+    p->wenc_hi = weh;
+    p->wenc_lo = wel;
+    p->wdec_hi = wdh;
+    p->wdec_lo = wdl;
+    p->c_hi = ch;
+    p->c_lo = cl;
+    p->g_hi = gh;
+    p->g_lo = gl;
+    p->dz_hi = dzh;
+    p->dz_lo = dzh + M * B * n;
+    p->dw_enc = dwe;
+    p->dw_dec = dwd;
+    p->part_enc = pe;
+    p->part_dec = pd;
+    p->db_part = dbp;
+    p->bnorm = bn;
+    p->l1_over_b = lob;
+    p->loss_stage = ls;
+    p->nnz_stage = ns;
+    p->tiles_mB_max = (int)tiles_mB;
+  }
+  return align_up(c.off, 1024);
+}
+
+// ------------------------------------------------------------------------------------------------
+// tensor maps for one batch size
+// ------------------------------------------------------------------------------------------------
+static int bn_for(int N) { return N > 128 ? 256 : 128; }
+constexpr int kBkDw = 32;  // K block of the MN-major weight-gradient GEMM
+
+static bool map2(CUtensorMap* hi, CUtensorMap* lo, const void* phi, const void* plo, uint64_t models,
+                 uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  return make_tmap_bf16(hi, phi, models, rows, cols, cols, rows * cols, box_rows) &&
+         make_tmap_bf16(lo, plo, models, rows, cols, cols, rows * cols, box_rows);
+}
+
+static int build_maps(sce_plan* p, int B, BatchMaps** out) {
+  auto it = p->maps->find(B);
+  if (it != p->maps->end()) {
+    *out = it->second;
+    return SCE_OK;
+  }
+  BatchMaps* m = new (std::nothrow) BatchMaps;
+  if (!m) return fail(SCE_ERR_INVALID, "out of host memory");
+  memset(m, 0, sizeof(*m));
+  const sce_desc& d = p->d;
+  const uint64_t M = d.n_models, n = d.n, dd = d.d, xm = p->xm, Bm = d.batch_max;
+  // NOTE: activations are laid out with the plan's batch_max pitch between models; only `B` rows are
+  // visible through the map, so rows >= B read as zero (TMA out-of-bounds fill).
+  auto act = [&](CUtensorMap* hi, CUtensorMap* lo, const void* phi, const void* plo, uint64_t models,
+                 uint64_t cols, uint32_t box_rows) {
+    return make_tmap_bf16(hi, phi, models, (uint64_t)B, cols, cols, Bm * cols, box_rows) &&
+           make_tmap_bf16(lo, plo, models, (uint64_t)B, cols, cols, Bm * cols, box_rows);
+  };
+  bool ok = true;
+  // encode: A = x [xm,B,d] K-major, B = Wenc [M,n,d] K-major
+  ok &= act(&m->encode.a_hi[0], &m->encode.a_lo[0], p->x_hi, p->x_lo, xm, dd, kBM);
+  ok &= map2(&m->encode.b_hi[0], &m->encode.b_lo[0], p->wenc_hi, p->wenc_lo, M, n, dd, bn_for(d.n));
+  // decode: A = c [M,B,n] K-major, B = Wdec [M,n,d] MN-major (box = 64 k-rows x 64 columns)
+  ok &= act(&m->decode.a_hi[0], &m->decode.a_lo[0], p->c_hi, p->c_lo, M, n, kBM);
+  ok &= map2(&m->decode.b_hi[0], &m->decode.b_lo[0], p->wdec_hi, p->wdec_lo, M, n, dd, 64);
+  // dcode: A = g [M,B,d] K-major, B = Wdec K-major
+  ok &= act(&m->dcode.a_hi[0], &m->dcode.a_lo[0], p->g_hi, p->g_lo, M, dd, kBM);
+  ok &= map2(&m->dcode.b_hi[0], &m->dcode.b_lo[0], p->wdec_hi, p->wdec_lo, M, n, dd, bn_for(d.n));
+  // weight gradients: everything MN-major, reduction over the batch rows
+  if (d.variant == SCE_UNTIED) {
+    ok &= act(&m->dw_enc.a_hi[0], &m->dw_enc.a_lo[0], p->dz_hi, p->dz_lo, M, n, kBkDw);
+    ok &= act(&m->dw_enc.b_hi[0], &m->dw_enc.b_lo[0], p->x_hi, p->x_lo, xm, dd, kBkDw);
+    ok &= act(&m->dw_dec.a_hi[0], &m->dw_dec.a_lo[0], p->c_hi, p->c_lo, M, n, kBkDw);
+    ok &= act(&m->dw_dec.b_hi[0], &m->dw_dec.b_lo[0], p->g_hi, p->g_lo, M, dd, kBkDw);
+  } else {
+    ok &= act(&m->dw_enc.a_hi[0], &m->dw_enc.a_lo[0], p->dz_hi, p->dz_lo, M, n, kBkDw);
+    ok &= act(&m->dw_enc.b_hi[0], &m->dw_enc.b_lo[0], p->x_hi, p->x_lo, xm, dd, kBkDw);
+    ok &= act(&m->dw_enc.a_hi[1], &m->dw_enc.a_lo[1], p->c_hi, p->c_lo, M, n, kBkDw);
+    ok &= act(&m->dw_enc.b_hi[1], &m->dw_enc.b_lo[1], p->g_hi, p->g_lo, M, dd, kBkDw);
+  }
+  if (!ok) {
+    delete m;
+    return fail(SCE_ERR_CUDA, "cuTensorMapEncodeTiled failed (B=%d, M=%d, n=%d, d=%d)", B, d.n_models, d.n, d.d);
+  }
+  (*p->maps)[B] = m;
+  *out = m;
+  return SCE_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// GEMM launcher
+// ------------------------------------------------------------------------------------------------
+template <class Epi, int BN, int BK, bool A_MN, bool B_MN, int STAGES>
+static int launch_gemm_t(const sce_plan* p, const GemmMaps& maps, int nsets, const int* a_batched,
+                         const int* b_batched, int k_total, int passes, int m_total, int n_total,
+                         const typename Epi::Params& epi, cudaStream_t st) {
+  using SM = GemmSmem<BN, BK, A_MN, B_MN, STAGES>;
+  auto kern = gemm_split_kernel<Epi, BN, BK, A_MN, B_MN, STAGES>;
+  static bool configured = false;
+  if (!configured) {
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kBytes));
+    configured = true;
+  }
+  GemmParams<typename Epi::Params> gp;
+  memset(&gp, 0, sizeof(gp));
+  for (int s = 0; s < nsets; ++s) {
+    gp.a_hi[s] = maps.a_hi[s];
+    gp.a_lo[s] = maps.a_lo[s];
+    gp.b_hi[s] = maps.b_hi[s];
+    gp.b_lo[s] = maps.b_lo[s];
+    gp.a_batched[s] = a_batched[s];
+    gp.b_batched[s] = b_batched[s];
+  }
+  gp.nsets = nsets;
+  gp.k_total = k_total;
+  gp.passes = passes;
+  gp.n_models = p->d.n_models;
+  gp.m_total = m_total;
+  gp.n_total = n_total;
+  gp.tiles_m = (m_total + kBM - 1) / kBM;
+  gp.tiles_n = (n_total + BN - 1) / BN;
+  gp.epi = epi;
+  const int tiles = gp.n_models * gp.tiles_m * gp.tiles_n;
+  const int grid = tiles < p->sms ? tiles : p->sms;
+  kern<<<grid, kGemmThreads, SM::kBytes, st>>>(gp);
+  CUDA_TRY(cudaGetLastError());
+  return SCE_OK;
+}
+
+// BN is chosen from the output width; K-major GEMMs use BK = 64, the MN-major one BK = kBkDw.
+#define SCE_DISPATCH_BN(N, CALL256, CALL128) ((N) > 128 ? (CALL256) : (CALL128))
+
+// ------------------------------------------------------------------------------------------------
+// helpers shared by step / forward / grads
+// ------------------------------------------------------------------------------------------------
+static AdamHyper hyper_for(const sce_plan* p, long long t) {
+  AdamHyper h;
+  h.lr = p->d.lr;
+  h.b1 = p->d.beta1;
+  h.b2 = p->d.beta2;
+  h.eps = p->d.eps;
+  h.eps_root = p->d.eps_root;
+  const double tt = p->d.adam_count_mode == SCE_ADAM_FROZEN_T1 ? 1.0 : (double)t;
+  h.bc1 = (float)(1.0 - pow((double)h.b1, tt));
+  h.bc2 = (float)(1.0 - pow((double)h.b2, tt));
+  return h;
+}
+
+template <int MODE>
+static int launch_dict_rows(float* e, const float* dw, float* m, float* v, __nv_bfloat16* hi, __nv_bfloat16* lo,
+                            float* grad_out, long long rows, int d, int normalize, float floor, AdamHyper h,
+                            cudaStream_t st) {
+  const int nv = (d + 511) / 512;
+  if (nv == 1)
+    dict_rows_kernel<1, MODE><<<(unsigned)rows, 128, 0, st>>>(e, dw, m, v, hi, lo, grad_out, d, normalize, floor, h);
+  else if (nv == 2)
+    dict_rows_kernel<2, MODE><<<(unsigned)rows, 128, 0, st>>>(e, dw, m, v, hi, lo, grad_out, d, normalize, floor, h);
+  else
+    dict_rows_kernel<4, MODE><<<(unsigned)rows, 128, 0, st>>>(e, dw, m, v, hi, lo, grad_out, d, normalize, floor, h);
+  CUDA_TRY(cudaGetLastError());
+  return SCE_OK;
+}
+
+__global__ void l1_over_b_kernel(const float* __restrict__ alpha, float* __restrict__ out, int M, float invB) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < M) out[i] = alpha ? alpha[i] * invB : 0.f;
+}
+
+// forward (+ optional backward GEMMs). Leaves dW in p->dw_enc / p->dw_dec when `backward`.
+static int run_pipeline(sce_plan* p, const float* x, int B, float* x_hat, bool backward, float* out_losses,
+                        float* out_nnz, cudaStream_t st) {
+  const sce_desc& d = p->d;
+  if (B < 1 || B > d.batch_max) return fail(SCE_ERR_INVALID, "B = %d outside [1, batch_max = %d]", B, d.batch_max);
+  if (!x) return fail(SCE_ERR_INVALID, "x is NULL");
+  BatchMaps* maps = nullptr;
+  int rc = build_maps(p, B, &maps);
+  if (rc) return rc;
+  int launches = 0;
+  const int M = d.n_models, n = d.n, dd = d.d;
+  const long long Bm = d.batch_max;
+  const int one[2] = {1, 1};
+  const int xb[2] = {d.x_per_model ? 1 : 0, 1};
+  const int tiles_mB = (B + kBM - 1) / kBM;
+
+  // ---- x -> (hi, lo): per model slabs are batch_max apart in the workspace
+  for (int m = 0; m < p->xm; ++m) {
+    const long long n4 = (long long)B * dd / 4;
+    const int blocks = (int)((n4 + 255) / 256 < 2048 ? (n4 + 255) / 256 : 2048);
+    split_rows_kernel<<<blocks, 256, 0, st>>>(x + (long long)m * B * dd, p->x_hi + m * Bm * dd,
+                                              p->x_lo + m * Bm * dd, n4);
+    ++launches;
+  }
+  CUDA_TRY(cudaGetLastError());
+  l1_over_b_kernel<<<(M + 127) / 128, 128, 0, st>>>(p->b.l1_alpha, p->l1_over_b, M, 1.0f / (float)B);
+  ++launches;
+
+  // ---- encode
+  int n_enc_parts;
+  if (d.variant != SCE_TOPK) {
+    EpiEncode::Params ep;
+    ep.bias = p->b.encoder_bias;
+    ep.mask = p->b.coef_mask;
+    ep.c_hi = p->c_hi;
+    ep.c_lo = p->c_lo;
+    ep.part = p->part_enc;
+    ep.c_model_stride = Bm * n;
+    ep.ldc = n;
+    ep.tiles_m = tiles_mB;
+    ep.flag_zero = 1;
+    if (n > 128) {
+      ep.tiles_n = (n + 255) / 256;
+      rc = launch_gemm_t<EpiEncode, 256, 64, false, false, 2>(p, maps->encode, 1, xb, one, dd, d.fwd_passes, B, n, ep, st);
+    } else {
+      ep.tiles_n = 1;
+      rc = launch_gemm_t<EpiEncode, 128, 64, false, false, 3>(p, maps->encode, 1, xb, one, dd, d.fwd_passes, B, n, ep, st);
+    }
+    if (rc) return rc;
+    ++launches;
+    n_enc_parts = tiles_mB * 4 * ep.tiles_n;
+  } else {
+    // scores -> fp32 (aliasing the dz pair), then per-row selection
+    EpiStoreF32::Params sp;
+    sp.out = reinterpret_cast<float*>(p->dz_hi);
+    sp.model_stride = Bm * n;
+    sp.ld = n;
+    if (n > 128)
+      rc = launch_gemm_t<EpiStoreF32, 256, 64, false, false, 2>(p, maps->encode, 1, xb, one, dd, d.fwd_passes, B, n, sp, st);
+    else
+      rc = launch_gemm_t<EpiStoreF32, 128, 64, false, false, 3>(p, maps->encode, 1, xb, one, dd, d.fwd_passes, B, n, sp, st);
+    if (rc) return rc;
+    ++launches;
+    if ((size_t)n * 4 > 200 * 1024) return fail(SCE_ERR_INVALID, "top-k: n = %d exceeds the shared-memory row buffer", n);
+    static bool cfg = false;
+    if (!cfg) {
+      CUDA_TRY(cudaFuncSetAttribute(topk_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      cfg = true;
+    }
+    // scores/codes of model m live at m * batch_max * n; the kernel indexes with B, so launch per model
+    for (int m = 0; m < M; ++m) {
+      topk_select_kernel<<<dim3(B, 1), 256, (size_t)n * 4, st>>>(
+          reinterpret_cast<const float*>(p->dz_hi) + (long long)m * Bm * n, p->b.sparsity + m,
+          p->c_hi + (long long)m * Bm * n, p->c_lo + (long long)m * Bm * n, p->part_enc + (long long)m * B * 2, B, n);
+      ++launches;
+    }
+    CUDA_TRY(cudaGetLastError());
+    n_enc_parts = B;
+  }
+
+  // ---- decode (+ residual, loss partial, g)
+  EpiDecode::Params dp;
+  dp.x = x;
+  dp.x_model_stride = d.x_per_model ? (long long)B * dd : 0;
+  dp.g_hi = p->g_hi;
+  dp.g_lo = p->g_lo;
+  dp.x_hat = x_hat;
+  dp.part = p->part_dec;
+  dp.g_model_stride = Bm * dd;
+  dp.xhat_model_stride = (long long)B * dd;
+  dp.ld = dd;
+  dp.tiles_m = tiles_mB;
+  dp.gscale = 2.0f / ((float)B * (float)dd);
+  if (dd > 128) {
+    dp.tiles_n = (dd + 255) / 256;
+    rc = launch_gemm_t<EpiDecode, 256, 64, false, true, 2>(p, maps->decode, 1, one, one, n, d.fwd_passes, B, dd, dp, st);
+  } else {
+    dp.tiles_n = 1;
+    rc = launch_gemm_t<EpiDecode, 128, 64, false, true, 3>(p, maps->decode, 1, one, one, n, d.fwd_passes, B, dd, dp, st);
+  }
+  if (rc) return rc;
+  ++launches;
+
+  // ---- losses
+  if (p->b.encoder_bias && p->b.bias_decay) {
+    bias_norm_kernel<<<M, 256, 0, st>>>(p->b.encoder_bias, n, p->bnorm);
+    ++launches;
+  }
+  finalize_kernel<<<M, 256, 0, st>>>(p->part_enc, n_enc_parts, p->part_dec, tiles_mB * 4 * dp.tiles_n, p->b.l1_alpha,
+                                     p->b.encoder_bias ? p->b.bias_decay : nullptr, p->bnorm, B, dd, out_losses, out_nnz);
+  ++launches;
+  CUDA_TRY(cudaGetLastError());
+
+  if (backward) {
+    // ---- dcode
+    EpiDcode::Params zp;
+    zp.c_hi = p->c_hi;
+    zp.l1_over_b = p->l1_over_b;
+    zp.dz_hi = p->dz_hi;
+    zp.dz_lo = p->dz_lo;
+    zp.db_part = p->b.encoder_bias ? p->db_part : nullptr;
+    zp.c_model_stride = Bm * n;
+    zp.ldc = n;
+    zp.tiles_m = tiles_mB;
+    if (n > 128)
+      rc = launch_gemm_t<EpiDcode, 256, 64, false, false, 2>(p, maps->dcode, 1, one, one, dd, d.bwd_passes, B, n, zp, st);
+    else
+      rc = launch_gemm_t<EpiDcode, 128, 64, false, false, 3>(p, maps->dcode, 1, one, one, dd, d.bwd_passes, B, n, zp, st);
+    if (rc) return rc;
+    ++launches;
+
+    // ---- weight gradients
+    auto dw = [&](const GemmMaps& gm, int nsets, const int* ab, const int* bb, float* out) -> int {
+      EpiStoreF32::Params sp;
+      sp.out = out;
+      sp.model_stride = (long long)n * dd;
+      sp.ld = dd;
+      if (dd > 128)
+        return launch_gemm_t<EpiStoreF32, 256, kBkDw, true, true, 4>(p, gm, nsets, ab, bb, B, d.bwd_passes, n, dd, sp, st);
+      return launch_gemm_t<EpiStoreF32, 128, kBkDw, true, true, 6>(p, gm, nsets, ab, bb, B, d.bwd_passes, n, dd, sp, st);
+    };
+    if (d.variant == SCE_UNTIED) {
+      rc = dw(maps->dw_enc, 1, one, xb, p->dw_enc);
+      if (rc) return rc;
+      rc = dw(maps->dw_dec, 1, one, one, p->dw_dec);
+      if (rc) return rc;
+      launches += 2;
+    } else {
+      const int bb[2] = {xb[0], 1};
+      rc = dw(maps->dw_enc, 2, one, bb, p->dw_enc);
+      if (rc) return rc;
+      ++launches;
+    }
+  }
+  p->last_launches = launches;
+  return SCE_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+int sce_version(void) { return SCE_VERSION; }
+const char* sce_last_error(void) { return g_err; }
+
+size_t sce_workspace_bytes(const sce_desc* desc) {
+  if (validate(desc)) return 0;
+  return carve(nullptr, *desc, nullptr);
+}
+
+int sce_plan_create(const sce_desc* desc, const sce_buffers* buffers, sce_plan** out_plan) {
+  if (!out_plan) return fail(SCE_ERR_INVALID, "out_plan is NULL");
+  *out_plan = nullptr;
+  int rc = validate(desc);
+  if (rc) return rc;
+  if (!buffers) return fail(SCE_ERR_INVALID, "buffers is NULL");
+  const sce_buffers& b = *buffers;
+  if (!b.encoder || !b.encoder_m || !b.encoder_v) return fail(SCE_ERR_INVALID, "encoder / encoder_m / encoder_v are required");
+  if (desc->variant == SCE_UNTIED && (!b.decoder || !b.decoder_m || !b.decoder_v))
+    return fail(SCE_ERR_INVALID, "untied variant needs decoder / decoder_m / decoder_v");
+  if (desc->variant != SCE_TOPK && (!b.encoder_bias || !b.bias_m || !b.bias_v))
+    return fail(SCE_ERR_INVALID, "encoder_bias / bias_m / bias_v are required for SAE variants");
+  if (desc->variant == SCE_TOPK && !b.sparsity) return fail(SCE_ERR_INVALID, "top-k variant needs the sparsity buffer");
+  const size_t need = carve(nullptr, *desc, nullptr);
+  if (!b.workspace || b.workspace_bytes < need)
+    return fail(SCE_ERR_WORKSPACE, "workspace too small: have %zu bytes, need %zu", b.workspace_bytes, need);
+  if (reinterpret_cast<uintptr_t>(b.workspace) % 1024)
+    return fail(SCE_ERR_WORKSPACE, "workspace must be 1024-byte aligned");
+  int dev = 0, major = 0, sms = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  CUDA_TRY(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  if (major != 10) return fail(SCE_ERR_NO_DEVICE, "libsce needs an sm_100 device (found compute capability %d.x)", major);
+  if (!get_encode_fn()) return fail(SCE_ERR_NO_DEVICE, "cuTensorMapEncodeTiled driver entry point not available");
+  sce_plan* p = new (std::nothrow) sce_plan;
+  if (!p) return fail(SCE_ERR_INVALID, "out of host memory");
+  memset(p, 0, sizeof(*p));
+  p->d = *desc;
+  p->b = b;
+  p->sms = sms;
+  p->xm = desc->x_per_model ? desc->n_models : 1;
+  p->maps = new std::map<int, BatchMaps*>();
+  carve(p, *desc, static_cast<uint8_t*>(b.workspace));
+  *out_plan = p;
+  return SCE_OK;
+}
+
+int sce_plan_destroy(sce_plan* plan) {
+  if (!plan) return SCE_OK;
+  for (auto& kv : *plan->maps) delete kv.second;
+  delete plan->maps;
+  delete plan;
+  return SCE_OK;
+}
+
+int sce_prepare(sce_plan* p, void* stream) {
+  if (!p) return fail(SCE_ERR_INVALID, "plan is NULL");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const sce_desc& d = p->d;
+  const long long rows = (long long)d.n_models * d.n;
+  AdamHyper h = hyper_for(p, 1);
+  int rc;
+  if (d.variant == SCE_UNTIED) {
+    rc = launch_dict_rows<MODE_PREPARE>(p->b.encoder, nullptr, nullptr, nullptr, p->wenc_hi, p->wenc_lo, nullptr, rows,
+                                        d.d, 0, 0.f, h, st);
+    if (rc) return rc;
+    rc = launch_dict_rows<MODE_PREPARE>(p->b.decoder, nullptr, nullptr, nullptr, p->wdec_hi, p->wdec_lo, nullptr, rows,
+                                        d.d, 1, d.norm_floor, h, st);
+  } else {
+    rc = launch_dict_rows<MODE_PREPARE>(p->b.encoder, nullptr, nullptr, nullptr, p->wenc_hi, p->wenc_lo, nullptr, rows,
+                                        d.d, 1, d.norm_floor, h, st);
+  }
+  return rc;
+}
+
+int sce_forward(sce_plan* p, const float* x, int B, float* x_hat, float* out_losses, float* out_nnz, void* stream) {
+  if (!p) return fail(SCE_ERR_INVALID, "plan is NULL");
+  return run_pipeline(p, x, B, x_hat, false, out_losses, out_nnz, static_cast<cudaStream_t>(stream));
+}
+
+int sce_step(sce_plan* p, const float* x, int B, float* out_losses, float* out_nnz, void* stream) {
+  if (!p) return fail(SCE_ERR_INVALID, "plan is NULL");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc = run_pipeline(p, x, B, nullptr, true, out_losses, out_nnz, st);
+  if (rc) return rc;
+  const sce_desc& d = p->d;
+  const long long rows = (long long)d.n_models * d.n;
+  p->step += 1;
+  const AdamHyper h = hyper_for(p, p->step);
+  int launches = p->last_launches;
+  if (d.variant == SCE_UNTIED) {
+    rc = launch_dict_rows<MODE_ADAM>(p->b.encoder, p->dw_enc, p->b.encoder_m, p->b.encoder_v, p->wenc_hi, p->wenc_lo,
+                                     nullptr, rows, d.d, 0, 0.f, h, st);
+    if (rc) return rc;
+    rc = launch_dict_rows<MODE_ADAM>(p->b.decoder, p->dw_dec, p->b.decoder_m, p->b.decoder_v, p->wdec_hi, p->wdec_lo,
+                                     nullptr, rows, d.d, 1, d.norm_floor, h, st);
+    if (rc) return rc;
+    launches += 2;
+  } else {
+    rc = launch_dict_rows<MODE_ADAM>(p->b.encoder, p->dw_enc, p->b.encoder_m, p->b.encoder_v, p->wenc_hi, p->wenc_lo,
+                                     nullptr, rows, d.d, 1, d.norm_floor, h, st);
+    if (rc) return rc;
+    ++launches;
+  }
+  if (p->b.encoder_bias) {
+    const long long tot = (long long)d.n_models * d.n;
+    const int n_part = ((B + kBM - 1) / kBM) * 4;
+    bias_kernel<MODE_ADAM><<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(
+        p->b.encoder_bias, p->b.bias_m, p->b.bias_v, p->db_part, n_part, d.n, d.n_models, p->b.bias_decay, p->bnorm,
+        nullptr, h);
+    CUDA_TRY(cudaGetLastError());
+    ++launches;
+  }
+  p->last_launches = launches;
+  return SCE_OK;
+}
+
+int sce_grads(sce_plan* p, const float* x, int B, float* d_encoder, float* d_bias, float* d_decoder,
+              float* out_losses, float* out_nnz, void* stream) {
+  if (!p) return fail(SCE_ERR_INVALID, "plan is NULL");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc = run_pipeline(p, x, B, nullptr, true, out_losses, out_nnz, st);
+  if (rc) return rc;
+  const sce_desc& d = p->d;
+  const long long rows = (long long)d.n_models * d.n;
+  const AdamHyper h = hyper_for(p, 1);
+  if (d.variant == SCE_UNTIED) {
+    if (d_encoder) {
+      rc = launch_dict_rows<MODE_GRAD>(p->b.encoder, p->dw_enc, nullptr, nullptr, nullptr, nullptr, d_encoder, rows, d.d,
+                                       0, 0.f, h, st);
+      if (rc) return rc;
+    }
+    if (d_decoder) {
+      rc = launch_dict_rows<MODE_GRAD>(p->b.decoder, p->dw_dec, nullptr, nullptr, nullptr, nullptr, d_decoder, rows, d.d,
+                                       1, d.norm_floor, h, st);
+      if (rc) return rc;
+    }
+  } else if (d_encoder) {
+    rc = launch_dict_rows<MODE_GRAD>(p->b.encoder, p->dw_enc, nullptr, nullptr, nullptr, nullptr, d_encoder, rows, d.d, 1,
+                                     d.norm_floor, h, st);
+    if (rc) return rc;
+  }
+  if (p->b.encoder_bias && d_bias) {
+    const long long tot = (long long)d.n_models * d.n;
+    const int n_part = ((B + kBM - 1) / kBM) * 4;
+    bias_kernel<MODE_GRAD><<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(
+        p->b.encoder_bias, nullptr, nullptr, p->db_part, n_part, d.n, d.n_models, p->b.bias_decay, p->bnorm, d_bias, h);
+    CUDA_TRY(cudaGetLastError());
+  }
+  return SCE_OK;
+}
+
+int sce_step_host(sce_plan* p, const float* x_host, int B, float* out_losses_host, float* out_nnz_host,
+                  void* stream) {
+  if (!p) return fail(SCE_ERR_INVALID, "plan is NULL");
+  if (!x_host) return fail(SCE_ERR_INVALID, "x_host is NULL");
+  if (B < 1 || B > p->d.batch_max) return fail(SCE_ERR_INVALID, "B = %d outside [1, batch_max = %d]", B, p->d.batch_max);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t bytes = (size_t)p->xm * B * p->d.d * sizeof(float);
+  CUDA_TRY(cudaMemcpyAsync(p->x_stage, x_host, bytes, cudaMemcpyHostToDevice, st));
+  int rc = sce_step(p, p->x_stage, B, p->loss_stage, p->nnz_stage, st);
+  if (rc) return rc;
+  if (out_losses_host)
+    CUDA_TRY(cudaMemcpyAsync(out_losses_host, p->loss_stage, (size_t)p->d.n_models * 4 * sizeof(float),
+                             cudaMemcpyDeviceToHost, st));
+  if (out_nnz_host)
+    CUDA_TRY(cudaMemcpyAsync(out_nnz_host, p->nnz_stage, (size_t)p->d.n_models * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return SCE_OK;
+}
+
+int sce_read_code(sce_plan* p, int B, float* out_code, void* stream) {
+  if (!p || !out_code) return fail(SCE_ERR_INVALID, "plan / out_code is NULL");
+  if (B < 1 || B > p->d.batch_max) return fail(SCE_ERR_INVALID, "B = %d outside [1, batch_max = %d]", B, p->d.batch_max);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long per = (long long)B * p->d.n;
+  for (int m = 0; m < p->d.n_models; ++m) {
+    const long long src = (long long)m * p->d.batch_max * p->d.n;
+    join_code_kernel<<<1024, 256, 0, st>>>(p->c_hi + src, p->c_lo + src, out_code + (long long)m * per, per / 2);
+  }
+  CUDA_TRY(cudaGetLastError());
+  return SCE_OK;
+}
+
+int sce_gather_rows(const void* chunk, int chunk_is_half, long long n_rows, int d, const long long* idx, int B,
+                    const float* sub, float* out, void* stream) {
+  if (!chunk || !out || B < 1 || d < 4 || d % 4) return fail(SCE_ERR_INVALID, "bad arguments to sce_gather_rows");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int blocks = (B + 7) / 8;
+  if (chunk_is_half)
+    gather_rows_kernel<__half><<<blocks, 256, 0, st>>>(static_cast<const __half*>(chunk), n_rows, d, idx, B, sub, out);
+  else
+    gather_rows_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float*>(chunk), n_rows, d, idx, B, sub, out);
+  CUDA_TRY(cudaGetLastError());
+  return SCE_OK;
+}
+
+int sce_last_launch_count(const sce_plan* plan) { return plan ? plan->last_launches : 0; }
+
+long long sce_get_step_count(const sce_plan* plan) { return plan ? plan->step : 0; }
+int sce_set_step_count(sce_plan* plan, long long steps_taken) {
+  if (!plan || steps_taken < 0) return fail(SCE_ERR_INVALID, "bad arguments to sce_set_step_count");
+  plan->step = steps_taken;
+  return SCE_OK;
+}
+
+}  // extern "C"

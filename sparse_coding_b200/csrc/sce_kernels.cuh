@@ -1,0 +1,446 @@
+// sce_kernels.cuh — the HBM-bound streaming kernels around the GEMMs of one training step:
+// batch split, dictionary normalise+split, row-norm Jacobian + Adam + re-split, bias Adam,
+// loss finalisation, top-k selection, code materialisation, chunk row gather.
+// Each is a single pass over its data with 16-byte accesses; algorithmic bytes per element are
+// listed in DESIGN.md.
+#pragma once
+#include "sce_ptx.cuh"
+
+namespace sce {
+
+// ------------------------------------------------------------------------------------------------
+// batch split: x fp32 [rows, d] -> (hi, lo) bf16
+// ------------------------------------------------------------------------------------------------
+__global__ void split_rows_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi,
+                                  __nv_bfloat16* __restrict__ lo, long long n4) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 v = reinterpret_cast<const float4*>(x)[i];
+    __nv_bfloat16 h[4], l[4];
+    split_bf16(v.x, h[0], l[0]);
+    split_bf16(v.y, h[1], l[1]);
+    split_bf16(v.z, h[2], l[2]);
+    split_bf16(v.w, h[3], l[3]);
+    reinterpret_cast<uint2*>(hi)[i] = make_uint2(pack_bf16(h[0], h[1]), pack_bf16(h[2], h[3]));
+    reinterpret_cast<uint2*>(lo)[i] = make_uint2(pack_bf16(l[0], l[1]), pack_bf16(l[2], l[3]));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// chunk row gather (+ fp16 -> fp32, + mean-centring): out[r,:] = float(chunk[idx[r],:]) - sub
+// one warp per row; big_sweep.py:168 and :359-364
+// ------------------------------------------------------------------------------------------------
+template <typename InT>
+__global__ void gather_rows_kernel(const InT* __restrict__ chunk, long long n_rows, int d,
+                                   const long long* __restrict__ idx, int B,
+                                   const float* __restrict__ sub, float* __restrict__ out) {
+  const int warps_per_block = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31;
+  for (int r = blockIdx.x * warps_per_block + (threadIdx.x >> 5); r < B; r += gridDim.x * warps_per_block) {
+    long long src = idx ? idx[r] : r;
+    if (src < 0) src += n_rows;
+    const InT* s = chunk + src * d;
+    float* o = out + (long long)r * d;
+    for (int c = lane * 4; c < d; c += 128) {
+      float v[4];
+      if constexpr (sizeof(InT) == 2) {
+        const uint2 raw = *reinterpret_cast<const uint2*>(s + c);
+        const __half2 a = *reinterpret_cast<const __half2*>(&raw.x);
+        const __half2 b = *reinterpret_cast<const __half2*>(&raw.y);
+        v[0] = __low2float(a);
+        v[1] = __high2float(a);
+        v[2] = __low2float(b);
+        v[3] = __high2float(b);
+      } else {
+        const float4 f = *reinterpret_cast<const float4*>(s + c);
+        v[0] = f.x;
+        v[1] = f.y;
+        v[2] = f.z;
+        v[3] = f.w;
+      }
+      if (sub) {
+        const float4 m = *reinterpret_cast<const float4*>(sub + c);
+        v[0] -= m.x;
+        v[1] -= m.y;
+        v[2] -= m.z;
+        v[3] -= m.w;
+      }
+      *reinterpret_cast<float4*>(o + c) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// block-wide sum over 128 threads (two values at once)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void block_sum2(float& a, float& b, float* red /*[8]*/) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+  }
+  const int w = threadIdx.x >> 5;
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) {
+    red[w] = a;
+    red[4 + w] = b;
+  }
+  __syncthreads();
+  a = red[0] + red[1] + red[2] + red[3];
+  b = red[4] + red[5] + red[6] + red[7];
+}
+
+struct AdamHyper {
+  float lr, b1, b2, eps, eps_root;
+  float bc1, bc2;  // 1 - b1^t, 1 - b2^t
+};
+
+__device__ __forceinline__ float adam_apply(float p, float g, float& m, float& v, const AdamHyper& h) {
+  m = h.b1 * m + (1.f - h.b1) * g;
+  v = h.b2 * v + (1.f - h.b2) * g * g;
+  const float mh = m / h.bc1;
+  const float vh = v / h.bc2;
+  return p - h.lr * (mh / (sqrtf(vh + h.eps_root) + h.eps));
+}
+
+// ------------------------------------------------------------------------------------------------
+// Dictionary rows: one 128-thread block per (model, row).
+//   MODE_PREPARE : w = e / max(||e||, floor) -> (w_hi, w_lo)                     (sce_prepare)
+//   MODE_ADAM    : de = J(dw); Adam on e; then as PREPARE for the updated row     (sce_step)
+//   MODE_GRAD    : de = J(dw) -> grad_out                                         (sce_grads)
+// J is the Jacobian of the row normalisation, de = (dw - w <w, dw>) / s (sae_ensemble.py:136-137
+// differentiated); with `normalize == 0` (untied encoder) J = I and the split is of e itself.
+// NV = ceil(d / 512) float4 per thread.
+// ------------------------------------------------------------------------------------------------
+enum { MODE_PREPARE = 0, MODE_ADAM = 1, MODE_GRAD = 2 };
+
+template <int NV, int MODE>
+__global__ void __launch_bounds__(128) dict_rows_kernel(float* __restrict__ e, const float* __restrict__ dw,
+                                                        float* __restrict__ m, float* __restrict__ v,
+                                                        __nv_bfloat16* __restrict__ w_hi,
+                                                        __nv_bfloat16* __restrict__ w_lo,
+                                                        float* __restrict__ grad_out, int d, int normalize,
+                                                        float floor, AdamHyper h) {
+  __shared__ float red[8];
+  const long long row = blockIdx.x;
+  const long long base = row * d;
+  float4 ev[NV], gv[NV];
+  float ss = 0.f, dot = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (i * 128 + threadIdx.x) * 4;
+    ev[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    gv[i] = ev[i];
+    if (c < d) {
+      ev[i] = *reinterpret_cast<const float4*>(e + base + c);
+      if (MODE != MODE_PREPARE) gv[i] = *reinterpret_cast<const float4*>(dw + base + c);
+    }
+    ss += ev[i].x * ev[i].x + ev[i].y * ev[i].y + ev[i].z * ev[i].z + ev[i].w * ev[i].w;
+    dot += ev[i].x * gv[i].x + ev[i].y * gv[i].y + ev[i].z * gv[i].z + ev[i].w * gv[i].w;
+  }
+  float s = 1.f;
+  if (normalize) {
+    block_sum2(ss, dot, red);
+    const float nrm = sqrtf(ss);
+    const bool clamped = floor > 0.f && nrm < floor;
+    s = clamped ? floor : nrm;
+    if (MODE != MODE_PREPARE) {
+      // <w, dw> = <e, dw> / s ;  de = (dw - w <w,dw>) / s = dw / s - e * <e,dw> / s^3
+      const float inv = 1.f / s;
+      const float k = clamped ? 0.f : dot * inv * inv * inv;  // clamp active: d s / d e = 0
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        gv[i].x = gv[i].x * inv - ev[i].x * k;
+        gv[i].y = gv[i].y * inv - ev[i].y * k;
+        gv[i].z = gv[i].z * inv - ev[i].z * k;
+        gv[i].w = gv[i].w * inv - ev[i].w * k;
+      }
+    }
+  }
+  if (MODE == MODE_GRAD) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (i * 128 + threadIdx.x) * 4;
+      if (c < d) *reinterpret_cast<float4*>(grad_out + base + c) = gv[i];
+    }
+    return;
+  }
+  if (MODE == MODE_ADAM) {
+    float ss2 = 0.f, dummy = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (i * 128 + threadIdx.x) * 4;
+      if (c < d) {
+        float4 mv = *reinterpret_cast<const float4*>(m + base + c);
+        float4 vv = *reinterpret_cast<const float4*>(v + base + c);
+        ev[i].x = adam_apply(ev[i].x, gv[i].x, mv.x, vv.x, h);
+        ev[i].y = adam_apply(ev[i].y, gv[i].y, mv.y, vv.y, h);
+        ev[i].z = adam_apply(ev[i].z, gv[i].z, mv.z, vv.z, h);
+        ev[i].w = adam_apply(ev[i].w, gv[i].w, mv.w, vv.w, h);
+        *reinterpret_cast<float4*>(m + base + c) = mv;
+        *reinterpret_cast<float4*>(v + base + c) = vv;
+        *reinterpret_cast<float4*>(e + base + c) = ev[i];
+        ss2 += ev[i].x * ev[i].x + ev[i].y * ev[i].y + ev[i].z * ev[i].z + ev[i].w * ev[i].w;
+      }
+    }
+    if (normalize) {
+      block_sum2(ss2, dummy, red);
+      const float nrm = sqrtf(ss2);
+      s = (floor > 0.f && nrm < floor) ? floor : nrm;
+    }
+  }
+  // emit the operand copy the next step's GEMMs read
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (i * 128 + threadIdx.x) * 4;
+    if (c < d) {
+      const float w[4] = {ev[i].x / s, ev[i].y / s, ev[i].z / s, ev[i].w / s};
+      __nv_bfloat16 hh[4], ll[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) split_bf16(w[u], hh[u], ll[u]);
+      *reinterpret_cast<uint2*>(w_hi + base + c) = make_uint2(pack_bf16(hh[0], hh[1]), pack_bf16(hh[2], hh[3]));
+      *reinterpret_cast<uint2*>(w_lo + base + c) = make_uint2(pack_bf16(ll[0], ll[1]), pack_bf16(ll[2], ll[3]));
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-model ||bias||_2  (bias-decay loss term and its gradient; sae_ensemble.py:73, :150)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) bias_norm_kernel(const float* __restrict__ bias, int n,
+                                                        float* __restrict__ out) {
+  __shared__ double red[8];
+  const float* b = bias + (long long)blockIdx.x * n;
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n; i += 256) acc += (double)b[i] * (double)b[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0;
+    for (int i = 0; i < 8; ++i) t += red[i];
+    out[blockIdx.x] = (float)sqrt(t);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// bias gradient = sum of the per-warp column partials (+ bias decay), then Adam or plain output
+// ------------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void bias_kernel(float* __restrict__ bias, float* __restrict__ m, float* __restrict__ v,
+                            const float* __restrict__ db_part, int n_part, int n, int n_models,
+                            const float* __restrict__ bias_decay, const float* __restrict__ bnorm,
+                            float* __restrict__ grad_out, AdamHyper h) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)n_models * n) return;
+  const int model = int(i / n);
+  const int j = int(i - (long long)model * n);
+  const float* p = db_part + (long long)model * n_part * n + j;
+  float g = 0.f;
+  for (int k = 0; k < n_part; ++k) g += p[(long long)k * n];
+  const float b = bias[i];
+  if (bias_decay) {
+    const float bd = bias_decay[model], nb = bnorm[model];
+    if (bd != 0.f && nb > 0.f) g += bd * b / nb;
+  }
+  if (MODE == MODE_GRAD) {
+    grad_out[i] = g;
+  } else {
+    float mm = m[i], vv = v[i];
+    bias[i] = adam_apply(b, g, mm, vv, h);
+    m[i] = mm;
+    v[i] = vv;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// losses: deterministic reduction of the GEMM epilogues' per-warp partials
+//   out[m] = {loss, l_reconstruction, l_l1, l_bias_decay}, nnz[m] = mean_b count_nonzero(c)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) finalize_kernel(const float* __restrict__ enc_part, int n_enc,
+                                                       const float* __restrict__ dec_part, int n_dec,
+                                                       const float* __restrict__ l1_alpha,
+                                                       const float* __restrict__ bias_decay,
+                                                       const float* __restrict__ bnorm, int B, int d,
+                                                       float* __restrict__ out, float* __restrict__ nnz) {
+  __shared__ double red[3][8];
+  const int model = blockIdx.x;
+  double l1 = 0, cnt = 0, sq = 0;
+  if (enc_part) {
+    const float* e = enc_part + (long long)model * n_enc * 2;
+    for (int i = threadIdx.x; i < n_enc; i += 256) {
+      l1 += e[2 * i];
+      cnt += e[2 * i + 1];
+    }
+  }
+  const float* dp = dec_part + (long long)model * n_dec;
+  for (int i = threadIdx.x; i < n_dec; i += 256) sq += dp[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    l1 += __shfl_xor_sync(0xffffffffu, l1, o);
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    red[0][threadIdx.x >> 5] = l1;
+    red[1][threadIdx.x >> 5] = cnt;
+    red[2][threadIdx.x >> 5] = sq;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0, b = 0, c = 0;
+    for (int i = 0; i < 8; ++i) {
+      a += red[0][i];
+      b += red[1][i];
+      c += red[2][i];
+    }
+    const float l_rec = (float)(c / ((double)B * d));
+    const float l_l1 = l1_alpha ? (float)(l1_alpha[model] * (a / B)) : 0.f;
+    const float l_bd = (bias_decay && bnorm) ? bias_decay[model] * bnorm[model] : 0.f;
+    if (out) {
+      out[model * 4 + 0] = l_rec + l_l1 + l_bd;
+      out[model * 4 + 1] = l_rec;
+      out[model * 4 + 2] = l_l1;
+      out[model * 4 + 3] = l_bd;
+    }
+    if (nnz) nnz[model] = (float)(b / B);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// dense fp32 code from its (hi, lo) pair (the -0.0 "z == 0" flag decodes to +0)
+// ------------------------------------------------------------------------------------------------
+__global__ void join_code_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo,
+                                 float* __restrict__ out, long long n2) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += stride) {
+    const __nv_bfloat162 h = reinterpret_cast<const __nv_bfloat162*>(hi)[i];
+    const __nv_bfloat162 l = reinterpret_cast<const __nv_bfloat162*>(lo)[i];
+    float2 o;
+    o.x = __low2float(h) + __low2float(l);
+    o.y = __high2float(h) + __high2float(l);
+    if (o.x == 0.f) o.x = 0.f;  // -0 -> +0
+    if (o.y == 0.f) o.y = 0.f;
+    reinterpret_cast<float2*>(out)[i] = o;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// TopK selection (topk_encoder.py:19-27): per row keep the k largest signed scores, ReLU, and emit
+// the dense (hi, lo) code the decode / weight-gradient GEMMs read, plus the nnz / partial sums.
+// One 256-thread block per (model, row); 4-pass 8-bit radix select on order-preserving keys.
+// Ties at the k-th value are broken by lowest column index (torch.topk leaves this unspecified, Q8).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t f2key(float f) {
+  const uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);  // ascending float order == ascending uint order
+}
+
+__global__ void __launch_bounds__(256) topk_select_kernel(const float* __restrict__ scores,
+                                                          const long long* __restrict__ sparsity,
+                                                          __nv_bfloat16* __restrict__ c_hi,
+                                                          __nv_bfloat16* __restrict__ c_lo,
+                                                          float* __restrict__ part /*[M][B][2]*/, int B, int n) {
+  extern __shared__ uint32_t keys[];  // n keys
+  __shared__ uint32_t hist[256];
+  __shared__ uint32_t sh_prefix, sh_remaining, sh_ties_before;
+  __shared__ float redf[16];
+  const int model = blockIdx.y;
+  const int row = blockIdx.x;
+  const long long base = ((long long)model * B + row) * n;
+  int k = (int)sparsity[model];
+  if (k > n) k = n;
+  for (int i = threadIdx.x; i < n; i += 256) keys[i] = f2key(scores[base + i]);
+  if (threadIdx.x == 0) {
+    sh_prefix = 0;
+    sh_remaining = (uint32_t)k;
+  }
+  __syncthreads();
+  // find the key of the k-th largest element
+  for (int pass = 0; pass < 4; ++pass) {
+    const int shift = 24 - 8 * pass;
+    hist[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t prefix = sh_prefix;
+    const uint32_t pmask = pass == 0 ? 0u : (0xFFFFFFFFu << (shift + 8));
+    for (int i = threadIdx.x; i < n; i += 256) {
+      const uint32_t kk = keys[i];
+      if ((kk & pmask) == prefix) atomicAdd(&hist[(kk >> shift) & 0xFF], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t rem = sh_remaining;
+      int b = 255;
+      for (; b > 0; --b) {
+        if (hist[b] >= rem) break;
+        rem -= hist[b];
+      }
+      sh_prefix = prefix | (uint32_t(b) << shift);
+      sh_remaining = rem;  // how many elements equal (so far) to the prefix must still be taken
+    }
+    __syncthreads();
+  }
+  const uint32_t kth = sh_prefix;          // exact key of the k-th largest
+  const uint32_t take_ties = sh_remaining; // number of elements == kth to keep (lowest index first)
+  float l1 = 0.f, cnt = 0.f;
+  // elements equal to kth: keep the first `take_ties` in index order (serial scan over chunks)
+  if (threadIdx.x == 0) sh_ties_before = 0;
+  __syncthreads();
+  for (int i0 = 0; i0 < n; i0 += 256) {
+    const int i = i0 + threadIdx.x;
+    uint32_t kk = 0;
+    bool is_tie = false;
+    if (i < n) {
+      kk = keys[i];
+      is_tie = kk == kth;
+    }
+    // rank of this tie among ties of the chunk
+    const uint32_t ball = __ballot_sync(0xffffffffu, is_tie);
+    __shared__ uint32_t warp_cnt[8];
+    if ((threadIdx.x & 31) == 0) warp_cnt[threadIdx.x >> 5] = __popc(ball);
+    __syncthreads();
+    uint32_t before = sh_ties_before;
+    for (int w = 0; w < (threadIdx.x >> 5); ++w) before += warp_cnt[w];
+    before += __popc(ball & ((1u << (threadIdx.x & 31)) - 1u));
+    if (i < n) {
+      const bool keep = kk > kth || (is_tie && before < take_ties);
+      const float s = scores[base + i];
+      const float cv = (keep && s > 0.f) ? s : 0.f;
+      __nv_bfloat16 h, l;
+      split_bf16(cv, h, l);
+      c_hi[base + i] = h;
+      c_lo[base + i] = l;
+      l1 += cv;
+      cnt += cv > 0.f ? 1.f : 0.f;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t t = 0;
+      for (int w = 0; w < 8; ++w) t += warp_cnt[w];
+      sh_ties_before += t;
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    l1 += __shfl_xor_sync(0xffffffffu, l1, o);
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    redf[threadIdx.x >> 5] = l1;
+    redf[8 + (threadIdx.x >> 5)] = cnt;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0, b = 0;
+    for (int w = 0; w < 8; ++w) {
+      a += redf[w];
+      b += redf[8 + w];
+    }
+    part[((long long)model * B + row) * 2] = a;
+    part[((long long)model * B + row) * 2 + 1] = b;
+  }
+}
+
+}  // namespace sce

@@ -1,0 +1,423 @@
+"""``FunctionalEnsemble`` — M sparse autoencoders trained in lock-step on one GPU.
+
+Drop-in for the reference's ``autoencoders/ensemble.py`` (FunctionalEnsemble :68-193, stack_dict/unstack_dict
+:50-65, optim_str_to_func :25-31): same constructor, same attributes (``params``, ``buffers``, ``optim_states``,
+``n_models``, ``sig``, ``device``, ``no_stacking``), same methods (``step_batch``, ``unstack``, ``state_dict`` /
+``from_state``, ``to_device``, ``to_shared_memory``). Parameters, buffers and Adam moments stay torch tensors owned
+by Python and are updated in place, so ``unstack``/export/IPC keep working.
+
+What differs is *how* a step is computed. The reference builds ``vmap(grad(sig.loss))`` + ``vmap(torchopt.adam)``
+out of ~70 stock PyTorch launches that stream the fp32 code tensor [M, B, n] through HBM a dozen times. Here
+``step_batch`` is one call into libsce.so (include/sce.h): four tcgen05 split-bf16 GEMMs with fused epilogues plus a
+handful of streaming kernels; the code tensor exists only as a (hi, lo) bf16 pair consumed by the next GEMM.
+``aux["c"]`` is therefore a lazy :class:`CodeProxy` — ``aux["c"].count_nonzero(dim=-1).float().mean(dim=-1)``
+(the only use in the reference loop, big_sweep.py:171) is answered from fused counters, and ``.dense()``
+materialises the real [M, B, n] tensor on demand.
+
+There is no CPU path and no generic-autograd path: a signature without an engine ``variant`` raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional
+
+import torch
+
+from . import _lib
+from .optim import AdamConfig, adam, resolve_optimizer
+from .signatures import DictSignature
+
+Tensor = torch.Tensor
+
+_VARIANT_CODE = {"tied": _lib.SCE_TIED, "masked_tied": _lib.SCE_TIED, "untied": _lib.SCE_UNTIED,
+                 "masked_untied": _lib.SCE_UNTIED, "topk": _lib.SCE_TOPK}
+_LOSS_KEYS = {
+    "tied": ("loss", "l_reconstruction", "l_l1"),
+    "masked_tied": ("loss", "l_reconstruction", "l_l1"),
+    "masked_untied": ("loss", "l_reconstruction", "l_l1"),
+    "untied": ("loss", "l_reconstruction", "l_l1", "l_bias_decay"),
+    "topk": ("loss",),
+}
+
+
+def optim_str_to_func(optim_str):
+    """ensemble.py:25-31."""
+    if optim_str == "adam":
+        return adam
+    raise ValueError("Unknown optimizer string: {}".format(optim_str))
+
+
+def construct_stacked_leaf(tensors, device=None) -> Tensor:
+    """ensemble.py:35-46."""
+    all_rg = all(t.requires_grad for t in tensors)
+    none_rg = all(not t.requires_grad for t in tensors)
+    if not all_rg and not none_rg:
+        raise RuntimeError("Expected tensors from each model to have the same .requires_grad")
+    result = torch.stack(list(tensors)).to(device=device)
+    if all_rg:
+        result = result.detach().requires_grad_()
+    return result
+
+
+def stack_dict(models: List[dict], device=None) -> dict:
+    """Stack the same-keyed (possibly nested) dicts of M models along a new dim 0 (ensemble.py:50-56)."""
+    first = models[0]
+    out = {}
+    for k, v in first.items():
+        if isinstance(v, dict):
+            out[k] = stack_dict([m[k] for m in models], device=device)
+        else:
+            out[k] = construct_stacked_leaf([m[k] for m in models], device=device)
+    return out
+
+
+def unstack_dict(params: dict, n_models: int, device=None) -> List[dict]:
+    """ensemble.py:59-65."""
+    outs = [dict() for _ in range(n_models)]
+    for k, v in params.items():
+        if isinstance(v, dict):
+            subs = unstack_dict(v, n_models, device=device)
+            for i in range(n_models):
+                outs[i][k] = subs[i]
+        else:
+            for i in range(n_models):
+                outs[i][k] = v[i].to(device=device)
+    return outs
+
+
+def _tree_map(fn, tree):
+    return {k: (_tree_map(fn, v) if isinstance(v, dict) else fn(v)) for k, v in tree.items()}
+
+
+class _RowCount:
+    """Result of ``CodeProxy.count_nonzero(dim=-1)``: supports the reference's ``.float().mean(dim=-1)``."""
+
+    def __init__(self, proxy):
+        self._p = proxy
+
+    def float(self):
+        return self
+
+    def mean(self, dim=-1):
+        if dim not in (-1, 1):
+            return self._p.dense().count_nonzero(dim=-1).float().mean(dim=dim)
+        return self._p.mean_nnz
+
+    def __getattr__(self, name):  # anything else: fall back to the real per-row counts
+        return getattr(self._p.dense().count_nonzero(dim=-1), name)
+
+
+class CodeProxy:
+    """Lazy stand-in for ``aux["c"]`` ([M, B, n] fp32). Valid until the next engine call on the ensemble."""
+
+    def __init__(self, ens, B, mean_nnz, serial):
+        self._ens, self._B, self.mean_nnz, self._serial = ens, B, mean_nnz, serial
+        self._dense = None
+
+    @property
+    def shape(self):
+        return torch.Size((self._ens.n_models, self._B, self._ens._n))
+
+    def count_nonzero(self, dim=-1):
+        if dim in (-1, 2):
+            return _RowCount(self)
+        return self.dense().count_nonzero(dim=dim)
+
+    def dense(self) -> Tensor:
+        if self._dense is None:
+            if self._serial != self._ens._serial:
+                raise RuntimeError("aux['c'] was read after a later engine call overwrote the code buffers; call "
+                                   ".dense() before the next step_batch, or construct the ensemble with "
+                                   "materialize_code=True")
+            self._dense = self._ens._read_code(self._B)
+        return self._dense
+
+    def __getattr__(self, name):
+        return getattr(self.dense(), name)
+
+    def __getitem__(self, idx):
+        return self.dense()[idx]
+
+
+class FunctionalEnsemble:
+    def __init__(self, models, sig, optimizer_func, optimizer_kwargs, device=None, no_stacking=False,
+                 adam_count_mode: str = "frozen_t1", fwd_passes: int = 3, bwd_passes: int = 3,
+                 materialize_code: bool = False):
+        """``models``: list of (params, buffers) from ``sig.init``; ``optimizer_func``: ``torchopt.adam`` (if
+        installed), :func:`sparse_coding_b200.optim.adam`, or the string "adam"; ``optimizer_kwargs``: ``{"lr": …}``.
+        ``no_stacking`` is accepted for API compatibility (the reference needs it for TopK because ``torch.topk``
+        with a data-dependent k cannot be vmapped; the engine batches TopK models natively).
+        Extra keywords (engine-only): ``adam_count_mode`` "frozen_t1" (reference behaviour) or
+        "standard"; ``fwd_passes`` / ``bwd_passes`` 3 (split-bf16, fp32-grade) or 1 (plain bf16)."""
+        if device is None:
+            first = next(iter(models[0][0].values()))
+            self.device = first.device
+        else:
+            self.device = device
+        self.n_models = len(models)
+        params, buffers = tuple(zip(*models))
+        self.params = stack_dict(list(params), device=self.device)
+        self.buffers = stack_dict(list(buffers), device=self.device)
+        self.sig = sig
+        self.no_stacking = no_stacking
+        self.optimizer_func = optimizer_func
+        self.optimizer_kwargs = optimizer_kwargs
+        self.optimizer = resolve_optimizer(optimizer_func, optimizer_kwargs)
+        self.adam_count_mode = adam_count_mode
+        self.fwd_passes, self.bwd_passes = fwd_passes, bwd_passes
+        self.materialize_code = materialize_code
+        self.optim_states = {
+            "mu": _tree_map(torch.zeros_like, self.params),
+            "nu": _tree_map(torch.zeros_like, self.params),
+            "count": _tree_map(lambda t: torch.zeros(t.shape[0], dtype=torch.int64, device=t.device), self.params),
+        }
+        self.init_functions()
+
+    # ------------------------------------------------------------------------------------------------------
+    def init_functions(self):
+        variant = getattr(self.sig, "variant", None)
+        if variant not in _VARIANT_CODE:
+            raise NotImplementedError(
+                f"{getattr(self.sig, '__name__', self.sig)} has no engine variant: only the signatures of the sweep hot "
+                "path (FunctionalTiedSAE, FunctionalSAE, the Masked variants, TopKEncoder) are implemented in the "
+                "sm_100a engine, and there is deliberately no generic autograd fallback")
+        self._variant = variant
+        self._plan = None
+        self._plan_key = None
+        self._ws = None
+        self._serial = 0
+        self._steps = 0
+        main = "dict" if variant == "topk" else "encoder"
+        self._main = main
+        self._n, self._d = self.params[main].shape[1], self.params[main].shape[2]
+        self._engine_buffers = None
+
+    # ------------------------------------------------------------------------------------------------------
+    # engine plumbing
+    # ------------------------------------------------------------------------------------------------------
+    def _require_cuda(self):
+        dev = torch.device(self.device)
+        if dev.type != "cuda":
+            raise RuntimeError(f"FunctionalEnsemble computes in the sm_100a CUDA engine; device is {dev}. "
+                               "Move it with to_device('cuda:…') — there is no CPU implementation.")
+        return dev
+
+    def _needs_centering(self) -> bool:
+        if self._variant != "tied":
+            return False
+        b = self.buffers
+        d = self._d
+        eye = torch.eye(d, device=b["center_rot"].device, dtype=b["center_rot"].dtype)
+        return not (bool((b["center_rot"] == eye).all()) and bool((b["center_trans"] == 0).all())
+                    and bool((b["center_scale"] == 1).all()))
+
+    def _build_plan(self, batch_max: int, x_per_model: bool):
+        dev = self._require_cuda()
+        lib = _lib.load()
+        for k, v in self.params.items():
+            if v.dtype != torch.float32:
+                raise TypeError(f"the engine trains fp32 parameters; params['{k}'] is {v.dtype}")
+            if not v.is_contiguous():
+                self.params[k] = v.contiguous()
+        self._destroy_plan()
+        cfg: AdamConfig = self.optimizer
+        desc = _lib.SceDesc(
+            variant=_VARIANT_CODE[self._variant], n_models=self.n_models, d=self._d, n=self._n,
+            batch_max=batch_max, x_per_model=int(x_per_model), lr=cfg.lr, beta1=cfg.b1, beta2=cfg.b2, eps=cfg.eps,
+            eps_root=cfg.eps_root,
+            adam_count_mode=_lib.SCE_ADAM_FROZEN_T1 if self.adam_count_mode == "frozen_t1" else _lib.SCE_ADAM_STANDARD,
+            fwd_passes=self.fwd_passes, bwd_passes=self.bwd_passes,
+            norm_floor=0.0 if self._variant == "topk" else 1e-8)
+        nbytes = lib.sce_workspace_bytes(C.byref(desc))
+        if nbytes == 0:
+            _lib.check(-1, "sce_workspace_bytes")
+        with torch.cuda.device(dev):
+            self._ws = torch.empty(nbytes + 1024, dtype=torch.uint8, device=dev)
+        ws_ptr = (self._ws.data_ptr() + 1023) // 1024 * 1024
+        M = self.n_models
+        eb = {}
+
+        def f32vec(name):  # [M] fp32 hyper-parameter buffers
+            t = self.buffers.get(name)
+            if t is None:
+                return None
+            eb[name] = t.to(device=dev, dtype=torch.float32).contiguous()
+            return eb[name].data_ptr()
+
+        ptr = lambda t: t.data_ptr() if t is not None else None
+        mu, nu = self.optim_states["mu"], self.optim_states["nu"]
+        bufs = _lib.SceBuffers()
+        bufs.encoder = ptr(self.params[self._main])
+        bufs.encoder_m, bufs.encoder_v = ptr(mu[self._main]), ptr(nu[self._main])
+        if self._variant != "topk":
+            bufs.encoder_bias = ptr(self.params["encoder_bias"])
+            bufs.bias_m, bufs.bias_v = ptr(mu["encoder_bias"]), ptr(nu["encoder_bias"])
+            bufs.l1_alpha = f32vec("l1_alpha")
+            if self._variant in ("tied", "untied"):
+                bufs.bias_decay = f32vec("bias_decay")
+        if self._variant in ("untied", "masked_untied"):
+            bufs.decoder = ptr(self.params["decoder"])
+            bufs.decoder_m, bufs.decoder_v = ptr(mu["decoder"]), ptr(nu["decoder"])
+        if self._variant in ("masked_tied", "masked_untied"):
+            eb["coef_mask"] = self.buffers["coef_mask"].to(device=dev, dtype=torch.uint8).contiguous()
+            bufs.coef_mask = eb["coef_mask"].data_ptr()
+        if self._variant == "topk":
+            eb["sparsity"] = self.buffers["sparsity"].to(device=dev, dtype=torch.int64).contiguous()
+            bufs.sparsity = eb["sparsity"].data_ptr()
+        bufs.workspace, bufs.workspace_bytes = ws_ptr, nbytes
+        plan = C.c_void_p()
+        with torch.cuda.device(dev):
+            _lib.check(lib.sce_plan_create(C.byref(desc), C.byref(bufs), C.byref(plan)), "sce_plan_create")
+            self._plan = plan
+            self._engine_buffers = eb
+            self._plan_key = (batch_max, bool(x_per_model))
+            _lib.check(lib.sce_set_step_count(plan, self._steps), "sce_set_step_count")
+            _lib.check(lib.sce_prepare(plan, self._stream()), "sce_prepare")
+        self._out_losses = torch.empty(M, _lib.SCE_LOSS_COLS, dtype=torch.float32, device=dev)
+        self._out_nnz = torch.empty(M, dtype=torch.float32, device=dev)
+
+    def _destroy_plan(self):
+        if getattr(self, "_plan", None) is not None:
+            _lib.load().sce_plan_destroy(self._plan)
+            self._plan = None
+
+    def __del__(self):
+        try:
+            self._destroy_plan()
+        except Exception:
+            pass
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(torch.device(self.device)).cuda_stream)
+
+    def _prep_batch(self, minibatches: Tensor, expand_dims: bool):
+        dev = self._require_cuda()
+        x = minibatches
+        if x.device != dev:
+            x = x.to(dev, non_blocking=True)
+        if x.dtype != torch.float32:
+            x = x.float()
+        per_model = not expand_dims
+        if self._needs_centering():
+            xe = x.expand(self.n_models, *x.shape) if expand_dims else x
+            b = self.buffers
+            x = torch.bmm(xe - b["center_trans"][:, None, :], b["center_rot"].transpose(1, 2)) * b["center_scale"][:, None, :]
+            per_model = True
+        x = x.contiguous()
+        B = x.shape[-2]
+        if x.shape[-1] != self._d or (per_model and x.shape[0] != self.n_models):
+            raise ValueError(f"batch shape {tuple(x.shape)} does not match ensemble (M={self.n_models}, d={self._d})")
+        key = self._plan_key
+        if self._plan is None or key is None or key[1] != per_model or B > key[0]:
+            self._build_plan(max(B, key[0]) if key else B, per_model)
+        return x, B
+
+    def _losses_dict(self) -> Dict[str, Tensor]:
+        cols = self._out_losses.clone()
+        return {k: cols[:, i] for i, k in enumerate(("loss", "l_reconstruction", "l_l1", "l_bias_decay"))
+                if k in _LOSS_KEYS[self._variant]}
+
+    def _aux(self, B):
+        self._serial += 1
+        proxy = CodeProxy(self, B, self._out_nnz.clone(), self._serial)
+        if self.materialize_code:
+            return {"c": proxy.dense()}
+        return {"c": proxy}
+
+    def _read_code(self, B) -> Tensor:
+        out = torch.empty(self.n_models, B, self._n, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(out.device):
+            _lib.check(_lib.load().sce_read_code(self._plan, B, out.data_ptr(), self._stream()), "sce_read_code")
+        return out
+
+    # ------------------------------------------------------------------------------------------------------
+    # public API (reference names)
+    # ------------------------------------------------------------------------------------------------------
+    def step_batch(self, minibatches, expand_dims=True):
+        """One Adam step of every model on one batch (ensemble.py:175-193). Returns (loss_data, aux)."""
+        with torch.no_grad():
+            x, B = self._prep_batch(minibatches, expand_dims)
+            with torch.cuda.device(x.device):
+                _lib.check(_lib.load().sce_step(self._plan, x.data_ptr(), B, self._out_losses.data_ptr(),
+                                                self._out_nnz.data_ptr(), self._stream()), "sce_step")
+            self._steps += 1
+            if self.adam_count_mode != "frozen_t1":
+                for t in self.optim_states["count"].values():
+                    t.add_(1)
+            return self._losses_dict(), self._aux(B)
+
+    def forward_batch(self, minibatches, expand_dims=True, return_x_hat=False):
+        """Forward only: losses and code statistics (and optionally x̂ [M,B,d]) without touching parameters."""
+        with torch.no_grad():
+            x, B = self._prep_batch(minibatches, expand_dims)
+            x_hat = torch.empty(self.n_models, B, self._d, dtype=torch.float32, device=x.device) if return_x_hat else None
+            with torch.cuda.device(x.device):
+                _lib.check(_lib.load().sce_forward(self._plan, x.data_ptr(), B,
+                                                   x_hat.data_ptr() if return_x_hat else None,
+                                                   self._out_losses.data_ptr(), self._out_nnz.data_ptr(),
+                                                   self._stream()), "sce_forward")
+            out = (self._losses_dict(), self._aux(B))
+            return out + (x_hat,) if return_x_hat else out
+
+    def grads_batch(self, minibatches, expand_dims=True):
+        """Parameter gradients exactly as ``vmap(grad(sig.loss))`` would return them (parity tests)."""
+        with torch.no_grad():
+            x, B = self._prep_batch(minibatches, expand_dims)
+            g = {k: torch.empty_like(v) for k, v in self.params.items()}
+            ptr = lambda k: g[k].data_ptr() if k in g else None
+            with torch.cuda.device(x.device):
+                _lib.check(_lib.load().sce_grads(self._plan, x.data_ptr(), B, ptr(self._main), ptr("encoder_bias"),
+                                                 ptr("decoder"), self._out_losses.data_ptr(),
+                                                 self._out_nnz.data_ptr(), self._stream()), "sce_grads")
+            return g, (self._losses_dict(), self._aux(B))
+
+    def refresh(self):
+        """Call after modifying ``params`` from outside the engine (re-derives the bf16 operand copies)."""
+        if self._plan is not None:
+            with torch.cuda.device(torch.device(self.device)):
+                _lib.check(_lib.load().sce_prepare(self._plan, self._stream()), "sce_prepare")
+
+    def gpu_launches_last_call(self) -> int:
+        return int(_lib.load().sce_last_launch_count(self._plan)) if self._plan is not None else 0
+
+    def unstack(self, device=None):
+        params = unstack_dict(self.params, self.n_models, device=device)
+        buffers = unstack_dict(self.buffers, self.n_models, device=device)
+        return list(zip(params, buffers))
+
+    def state_dict(self):
+        """ensemble.py:150-161 keys, plus the engine-only settings."""
+        return {
+            "device": self.device, "n_models": self.n_models, "params": self.params, "buffers": self.buffers,
+            "sig": self.sig, "no_stacking": self.no_stacking, "optimizer_func": self.optimizer_func,
+            "optimizer_kwargs": self.optimizer_kwargs, "optim_states": self.optim_states,
+            "adam_count_mode": self.adam_count_mode, "fwd_passes": self.fwd_passes, "bwd_passes": self.bwd_passes,
+            "materialize_code": self.materialize_code, "steps": self._steps,
+        }
+
+    @staticmethod
+    def from_state(state_dict):
+        self = FunctionalEnsemble.__new__(FunctionalEnsemble)
+        for k in ("device", "n_models", "params", "buffers", "sig", "no_stacking", "optimizer_func",
+                  "optimizer_kwargs", "optim_states"):
+            setattr(self, k, state_dict[k])
+        self.adam_count_mode = state_dict.get("adam_count_mode", "frozen_t1")
+        self.fwd_passes = state_dict.get("fwd_passes", 3)
+        self.bwd_passes = state_dict.get("bwd_passes", 3)
+        self.materialize_code = state_dict.get("materialize_code", False)
+        self.optimizer = resolve_optimizer(self.optimizer_func, self.optimizer_kwargs)
+        self.init_functions()
+        self._steps = state_dict.get("steps", 0)
+        return self
+
+    def to_device(self, device):
+        self._destroy_plan()
+        self._plan_key = None
+        self.device = device
+        self.params = _tree_map(lambda t: t.to(device), self.params)
+        self.buffers = _tree_map(lambda t: t.to(device), self.buffers)
+        self.optim_states = _tree_map(lambda t: t.to(device), self.optim_states)
+
+    def to_shared_memory(self):
+        for tree in (self.params, self.buffers, self.optim_states):
+            _tree_map(lambda t: t.share_memory_(), tree)
