@@ -1,0 +1,314 @@
+#!/usr/bin/env python
+"""bench.py — throughput of the ensemble-SAE training hot path (BASELINE.json metric: activations/sec/GPU).
+
+    python bench.py --gpus N --steps K --warmup W            # this engine
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's own CPU PyTorch path
+
+A "step" is one ``FunctionalEnsemble.step_batch`` over one batch of synthetic activations: forward, losses,
+backward and the Adam update of every model of the ensemble (nothing is skipped or cached). The workload at N=1 is
+BASELINE config 2: 16 tied SAEs, d_model=512, dict_ratio=8 (n=4096), L1 = logspace(-4,-2,16), batch 8192, fp32
+parameters, lr 1e-3. For N>1 every rank trains its own 16-model shard on the same activation stream (config 4:
+model-axis sharding, no data-path collective) — weak scaling; value = rows consumed by all ranks' shards per second.
+
+Printed JSON (one line, rank 0): the driver contract plus
+  roofline      dominant kernel (weight-gradient GEMM): algorithmic FLOPs / CUDA-event time vs the measured bf16 peak
+  cpu_baseline  the oracle port of the reference step on this box's host cores, bounded sample
+  e2e           same metric through the public API with HOST (pinned) batches: H2D copy + step + D2H of the losses
+  phases_ms     per-phase device time of a step (events recorded inside libsce on the launching stream)
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (M, d, n, B, description)
+    "cfg2": (16, 512, 4096, 8192, "16 TiedSAE d_model=512 dict_ratio=8 L1=logspace(-4,-2,16) batch=8192 (BASELINE configs[1])"),
+    "cfg1": (1, 128, 256, 1024, "1 TiedSAE d_model=128 dict_ratio=2 L1=1e-3 batch=1024 (BASELINE configs[0])"),
+    "cfg5": (1, 2048, 32768, 4096, "1 TiedSAE/GPU d_model=2048 dict_ratio=16 batch=4096 (BASELINE configs[4])"),
+}
+METRIC = "activations/sec (whole job; rows consumed by every resident model)"
+
+
+def l1_grid(M):
+    return [1e-3] if M == 1 else [float(a) for a in np.logspace(-4, -2, M)]
+
+
+def make_models(sig, M, d, n, seed):
+    torch.manual_seed(seed)
+    return [sig.init(d, n, a) for a in l1_grid(M)]
+
+
+def synth_batches(n_batches, B, d, seed, pin=False):
+    """Sparse-mixture activations (the distribution of sc_datasets/random_dataset.py:76-142): a few unit features
+    per row + noise, so that ReLU sparsity is non-trivial. Returns CPU tensors."""
+    gen = torch.Generator().manual_seed(seed)
+    feats = torch.randn(2048, d, generator=gen)
+    feats /= feats.norm(dim=-1, keepdim=True)
+    out = []
+    for _ in range(n_batches):
+        codes = (torch.rand(B, 2048, generator=gen) < 0.01).float() * torch.rand(B, 2048, generator=gen)
+        x = codes @ feats + 0.05 * torch.randn(B, d, generator=gen)
+        out.append(x.pin_memory() if pin else x)
+    return out
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.path = tempfile.mktemp(suffix=".csv")
+        self.gpu = gpu_index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.QUERY}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            f = [t.strip() for t in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+                power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "power_w_max": float(max(power)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"bf16_tflops": p.get("bf16_tflops_sustained", p.get("bf16_tflops")), "hbm_gbs": p.get("hbm_gbs"),
+                "source": "measured (MEASURED_PEAKS.json, sustained bf16)"}
+    return {"bf16_tflops": 1400.0, "hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# CPU arm: the reference's own PyTorch path (oracle port) on host cores
+# ----------------------------------------------------------------------------------------------------------------
+def cpu_reference_rate(M, d, n, B_full, budget_s=20.0, steps=1, warmup=1):
+    """Times ``steps`` steps of the restated reference (vmap(grad(loss)) + Adam, fp32, all host threads) on a
+    bounded sample: the full ensemble at a reduced batch chosen so that the work fits the budget. Returns
+    (activations/s, description, cores)."""
+    from oracle import sae_oracle as O
+    from sparse_coding_b200 import FunctionalTiedSAE
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    models = make_models(FunctionalTiedSAE, M, d, n, 0)
+    ens = O.RefPortEnsemble(models, O.SIG_LOSSES["tied"], lr=1e-3)
+    # probe at a small batch to size the sample
+    Bp = min(B_full, 256)
+    chunk = synth_batches(1, max(Bp, 64), d, 123)[0]
+    idx = torch.randperm(chunk.shape[0])[:Bp]
+    t0 = time.perf_counter()
+    ens.step_batch(chunk[idx])
+    probe = time.perf_counter() - t0
+    per_row = probe / Bp
+    Bs = int(min(B_full, max(Bp, budget_s / max(steps + warmup, 1) / per_row)))
+    Bs = max(64, (Bs // 64) * 64)
+    # bound the [M,B,n] fp32 temporaries (about 12 live copies) to ~24 GB of host memory
+    Bs = min(Bs, max(64, int(24e9 / (12 * 4 * M * n)) // 64 * 64))
+    chunk = synth_batches(1, Bs, d, 124)[0]
+    for _ in range(warmup):
+        ens.step_batch(chunk[torch.randperm(Bs)])      # includes the reference's CPU gather (big_sweep.py:168)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        ens.step_batch(chunk[torch.randperm(Bs)])
+    dt = (time.perf_counter() - t0) / steps
+    return Bs / dt, f"{steps} step(s) of the full {M}-model ensemble at batch {Bs} of {B_full} rows (fp32, torch CPU)", cores, dt
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    M, d, n, B, desc = WORKLOADS[args.workload]
+    rate, sample, cores, dt = cpu_reference_rate(M, d, n, B, budget_s=60.0, steps=max(args.steps, 1),
+                                                 warmup=max(args.warmup, 1))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": "activations/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {desc}", "parallelism": "host CPU threads"},
+        "cpu_baseline": {"value": rate, "unit": "activations/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": "activations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--bwd-passes", type=int, default=3, choices=[1, 3])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch.distributed as dist
+    import sparse_coding_b200 as S
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the engine has no CPU path)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    M, d, n, B, desc = WORKLOADS[args.workload]
+    K, W = args.steps, max(args.warmup, 3)
+
+    # every rank owns its own shard of the sweep: same shapes, different seeds (model-axis sharding)
+    ens = S.FunctionalEnsemble(make_models(S.FunctionalTiedSAE, M, d, n, seed=rank), S.FunctionalTiedSAE, S.adam,
+                               {"lr": 1e-3}, device=dev, bwd_passes=args.bwd_passes)
+    n_pool = 8
+    host = synth_batches(n_pool, B, d, seed=1000, pin=True)        # identical stream on every rank
+    pool = [x.to(dev) for x in host]                                 # resident copies for the device-timed run
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident run: `value`
+    for i in range(W):
+        ens.step_batch(pool[i % n_pool])
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ens.profile_begin()
+    launches = 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(K):
+        losses, aux = ens.step_batch(pool[i % n_pool])
+        launches += ens.gpu_launches_last_call()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    phases = ens.profile_end()
+    clocks = sampler.stop() if rank == 0 else None
+    final_loss = losses["loss"].detach().clone()
+
+    # ---------------- end-to-end run through the public API with host batches: `e2e`
+    barrier()
+    h2d = B * d * 4
+    d2h = 0
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for i in range(2):
+        ens.step_batch(host[i % n_pool])
+    barrier()
+    e2.record()
+    for i in range(K):
+        losses, aux = ens.step_batch(host[i % n_pool])               # pinned host -> device copy inside
+        got = {k: v.cpu() for k, v in losses.items()}                 # D2H of the step's result
+        nnz = aux["c"].count_nonzero(dim=-1).float().mean(dim=-1).cpu()
+    e3.record()
+    barrier()
+    ms_e2e = e2.elapsed_time(e3)
+    d2h = sum(v.numel() * 4 for v in got.values()) + nnz.numel() * 4
+
+    t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        # end-of-chunk metric gather (the only collective on this path): every model's final loss to every rank
+        gathered = [torch.empty_like(final_loss) for _ in range(world)]
+        dist.all_gather(gathered, final_loss)
+        final_loss = torch.cat(gathered)
+    ms, ms_e2e = float(t[0]), float(t[1])
+
+    if rank == 0:
+        pk = peaks()
+        value = world * B * K / (ms * 1e-3)
+        e2e_value = world * B * K / (ms_e2e * 1e-3)
+        steps_prof = max(phases["steps"], 1)
+        per_phase = {k: v / steps_prof for k, v in phases.items() if k != "steps"}
+        dw_ms = per_phase["dw"]
+        alg_flops_dw = 4.0 * M * B * n * d            # dW = dz^T x + c^T g: two GEMMs of 2*B*n*d per model
+        achieved = alg_flops_dw / (dw_ms * 1e-3) / 1e12 if dw_ms > 0 else None
+        step_flops = 10.0 * M * B * n * d
+        line = {
+            "metric": METRIC, "value": value, "unit": "activations/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 (parameters, accumulation; products on the bf16 tensor pipe as hi/lo split pairs)",
+            "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {desc}", "models_per_gpu": M, "d_model": d, "dict_size": n,
+                       "batch": B, "parallelism": f"ensemble-shard x{world}" if world > 1 else "single GPU",
+                       "fwd_passes": 3, "bwd_passes": args.bwd_passes, "adam_count_mode": "frozen_t1",
+                       "l2": "per-step working set (code + code-gradient, 4.3 GB) and the 8-batch input pool "
+                             "(134 MB) both exceed the 126 MB L2; no explicit flush"},
+            "clocks": clocks, "gpu_launches": launches,
+            "e2e": {"value": e2e_value, "unit": "activations/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e / K},
+            "roofline": {"bound": "tensor", "kernel": "gemm_split_kernel<EpiStoreF32,MN,MN> (weight gradient)",
+                         "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
+                         "frac": achieved / pk["bf16_tflops"] if achieved else None, "traffic": None,
+                         "peak_source": pk["source"], "alg_flops_per_launch": alg_flops_dw,
+                         "ms_per_launch": dw_ms,
+                         "issued_tflops": alg_flops_dw * args.bwd_passes / (dw_ms * 1e-3) / 1e12 if dw_ms > 0 else None,
+                         "step_alg_tflops": step_flops / (ms / K * 1e-3) / 1e12},
+            "phases_ms": per_phase,
+            "final_loss_mean": float(final_loss.mean()),
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            rate, sample, cores, _ = cpu_reference_rate(M, d, n, B, budget_s=20.0)
+            line["cpu_baseline"] = {"value": rate, "unit": "activations/s", "cores": cores, "kind": "port",
+                                    "sample": sample}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -131,6 +131,22 @@ int sce_grads(sce_plan* plan, const float* x, int B, float* d_encoder, float* d_
 int sce_gather_rows(const void* chunk, int chunk_is_half, long long n_rows, int d, const long long* idx, int B,
                     const float* sub, float* out, void* stream);
 
+/* Per-phase device timing of sce_step, measured with CUDA events recorded on the caller's stream between the
+ * kernels of a step (bench.py's roofline). Between sce_profile_begin and sce_profile_end up to 64 steps are
+ * recorded; sce_profile_end synchronises and returns the summed milliseconds of each phase. */
+enum {
+  SCE_PHASE_SPLIT = 0,  /* batch -> (hi, lo) */
+  SCE_PHASE_ENCODE = 1, /* encode GEMM (+ top-k selection) */
+  SCE_PHASE_DECODE = 2, /* decode GEMM + residual */
+  SCE_PHASE_LOSSES = 3, /* bias norm + loss finalisation */
+  SCE_PHASE_DCODE = 4,  /* code-gradient GEMM */
+  SCE_PHASE_DW = 5,     /* weight-gradient GEMM(s) */
+  SCE_PHASE_ADAM = 6,   /* Jacobian + Adam + renormalise + re-split, bias Adam */
+  SCE_PHASE_COUNT = 7
+};
+int sce_profile_begin(sce_plan* plan);
+int sce_profile_end(sce_plan* plan, float* phase_ms /*[SCE_PHASE_COUNT]*/, int* steps_recorded);
+
 /* Optimiser step counter (number of sce_step calls so far); settable so a resumed run keeps the bias correction
  * of SCE_ADAM_STANDARD continuous. */
 long long sce_get_step_count(const sce_plan* plan);

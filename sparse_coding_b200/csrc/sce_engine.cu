@@ -68,7 +68,17 @@ struct sce_plan {
   std::map<int, BatchMaps*>* maps;
   int last_launches;
   long long step;  // number of optimiser steps taken
+  // optional per-phase device timing (sce_profile_*): events bracket each phase of a step
+  bool prof_on;
+  int prof_steps;                          // steps recorded since sce_profile_begin
+  cudaEvent_t* prof_ev;                    // [kProfMaxSteps][SCE_PHASE_COUNT + 1]
 };
+
+constexpr int kProfMaxSteps = 64;
+static inline void prof_mark(sce_plan* p, int idx, cudaStream_t st) {
+  if (p->prof_on && p->prof_steps < kProfMaxSteps)
+    cudaEventRecord(p->prof_ev[p->prof_steps * (SCE_PHASE_COUNT + 1) + idx], st);
+}
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -314,6 +324,7 @@ static int run_pipeline(sce_plan* p, const float* x, int B, float* x_hat, bool b
   const int xb[2] = {d.x_per_model ? 1 : 0, 1};
   const int tiles_mB = (B + kBM - 1) / kBM;
 
+  prof_mark(p, SCE_PHASE_SPLIT, st);
   // ---- x -> (hi, lo): per model slabs are batch_max apart in the workspace
   for (int m = 0; m < p->xm; ++m) {
     const long long n4 = (long long)B * dd / 4;
@@ -327,6 +338,7 @@ static int run_pipeline(sce_plan* p, const float* x, int B, float* x_hat, bool b
   ++launches;
 
   // ---- encode
+  prof_mark(p, SCE_PHASE_ENCODE, st);
   int n_enc_parts;
   if (d.variant != SCE_TOPK) {
     EpiEncode::Params ep;
@@ -379,6 +391,7 @@ static int run_pipeline(sce_plan* p, const float* x, int B, float* x_hat, bool b
   }
 
   // ---- decode (+ residual, loss partial, g)
+  prof_mark(p, SCE_PHASE_DECODE, st);
   EpiDecode::Params dp;
   dp.x = x;
   dp.x_model_stride = d.x_per_model ? (long long)B * dd : 0;
@@ -402,6 +415,7 @@ static int run_pipeline(sce_plan* p, const float* x, int B, float* x_hat, bool b
   ++launches;
 
   // ---- losses
+  prof_mark(p, SCE_PHASE_LOSSES, st);
   if (p->b.encoder_bias && p->b.bias_decay) {
     bias_norm_kernel<<<M, 256, 0, st>>>(p->b.encoder_bias, n, p->bnorm);
     ++launches;
@@ -411,6 +425,7 @@ static int run_pipeline(sce_plan* p, const float* x, int B, float* x_hat, bool b
   ++launches;
   CUDA_TRY(cudaGetLastError());
 
+  prof_mark(p, SCE_PHASE_DCODE, st);
   if (backward) {
     // ---- dcode
     EpiDcode::Params zp;
@@ -430,6 +445,7 @@ static int run_pipeline(sce_plan* p, const float* x, int B, float* x_hat, bool b
     ++launches;
 
     // ---- weight gradients
+    prof_mark(p, SCE_PHASE_DW, st);
     auto dw = [&](const GemmMaps& gm, int nsets, const int* ab, const int* bb, float* out) -> int {
       EpiStoreF32::Params sp;
       sp.out = out;
@@ -452,6 +468,7 @@ static int run_pipeline(sce_plan* p, const float* x, int B, float* x_hat, bool b
       ++launches;
     }
   }
+  prof_mark(p, SCE_PHASE_ADAM, st);
   p->last_launches = launches;
   return SCE_OK;
 }
@@ -510,6 +527,10 @@ int sce_plan_destroy(sce_plan* plan) {
   if (!plan) return SCE_OK;
   for (auto& kv : *plan->maps) delete kv.second;
   delete plan->maps;
+  if (plan->prof_ev) {
+    for (int i = 0; i < kProfMaxSteps * (SCE_PHASE_COUNT + 1); ++i) cudaEventDestroy(plan->prof_ev[i]);
+    free(plan->prof_ev);
+  }
   delete plan;
   return SCE_OK;
 }
@@ -572,6 +593,8 @@ int sce_step(sce_plan* p, const float* x, int B, float* out_losses, float* out_n
     CUDA_TRY(cudaGetLastError());
     ++launches;
   }
+  prof_mark(p, SCE_PHASE_COUNT, st);
+  if (p->prof_on && p->prof_steps < kProfMaxSteps) p->prof_steps += 1;
   p->last_launches = launches;
   return SCE_OK;
 }
@@ -657,6 +680,36 @@ int sce_gather_rows(const void* chunk, int chunk_is_half, long long n_rows, int 
 }
 
 int sce_last_launch_count(const sce_plan* plan) { return plan ? plan->last_launches : 0; }
+
+int sce_profile_begin(sce_plan* p) {
+  if (!p) return fail(SCE_ERR_INVALID, "plan is NULL");
+  if (!p->prof_ev) {
+    const int n = kProfMaxSteps * (SCE_PHASE_COUNT + 1);
+    p->prof_ev = static_cast<cudaEvent_t*>(calloc(n, sizeof(cudaEvent_t)));
+    if (!p->prof_ev) return fail(SCE_ERR_INVALID, "out of host memory");
+    for (int i = 0; i < n; ++i) CUDA_TRY(cudaEventCreate(&p->prof_ev[i]));
+  }
+  p->prof_steps = 0;
+  p->prof_on = true;
+  return SCE_OK;
+}
+
+int sce_profile_end(sce_plan* p, float* phase_ms, int* steps_recorded) {
+  if (!p || !phase_ms) return fail(SCE_ERR_INVALID, "plan / phase_ms is NULL");
+  p->prof_on = false;
+  for (int k = 0; k < SCE_PHASE_COUNT; ++k) phase_ms[k] = 0.f;
+  for (int s = 0; s < p->prof_steps; ++s) {
+    cudaEvent_t* ev = p->prof_ev + s * (SCE_PHASE_COUNT + 1);
+    CUDA_TRY(cudaEventSynchronize(ev[SCE_PHASE_COUNT]));
+    for (int k = 0; k < SCE_PHASE_COUNT; ++k) {
+      float ms = 0.f;
+      CUDA_TRY(cudaEventElapsedTime(&ms, ev[k], ev[k + 1]));
+      phase_ms[k] += ms;
+    }
+  }
+  if (steps_recorded) *steps_recorded = p->prof_steps;
+  return SCE_OK;
+}
 
 long long sce_get_step_count(const sce_plan* plan) { return plan ? plan->step : 0; }
 int sce_set_step_count(sce_plan* plan, long long steps_taken) {

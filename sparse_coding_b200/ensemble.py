@@ -377,6 +377,21 @@ class FunctionalEnsemble:
             with torch.cuda.device(torch.device(self.device)):
                 _lib.check(_lib.load().sce_prepare(self._plan, self._stream()), "sce_prepare")
 
+    def profile_begin(self):
+        """Start per-phase device timing of the following ``step_batch`` calls (up to 64 steps)."""
+        if self._plan is None:
+            raise RuntimeError("profile_begin needs a built plan: run one step_batch first")
+        _lib.check(_lib.load().sce_profile_begin(self._plan), "sce_profile_begin")
+
+    def profile_end(self) -> Dict[str, float]:
+        """Stop timing; returns {"steps": k, phase: total milliseconds over those k steps, ...}."""
+        ms = (C.c_float * len(_lib.PHASES))()
+        steps = C.c_int(0)
+        _lib.check(_lib.load().sce_profile_end(self._plan, ms, C.byref(steps)), "sce_profile_end")
+        out = {name: float(ms[i]) for i, name in enumerate(_lib.PHASES)}
+        out["steps"] = int(steps.value)
+        return out
+
     def gpu_launches_last_call(self) -> int:
         return int(_lib.load().sce_last_launch_count(self._plan)) if self._plan is not None else 0
 
