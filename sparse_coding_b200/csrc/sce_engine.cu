@@ -236,7 +236,7 @@ template <class Epi, int BN, int BK, bool A_MN, bool B_MN, int STAGES>
 static int launch_gemm_t(const sce_plan* p, const GemmMaps& maps, int nsets, const int* a_batched,
                          const int* b_batched, int k_total, int passes, int m_total, int n_total,
                          const typename Epi::Params& epi, cudaStream_t st) {
-  using SM = GemmSmem<BN, BK, A_MN, B_MN, STAGES>;
+  using SM = GemmSmem<BN, BK, A_MN, B_MN, STAGES, Epi::kWarpStageBytes>;
   auto kern = gemm_split_kernel<Epi, BN, BK, A_MN, B_MN, STAGES>;
   static bool configured = false;
   if (!configured) {

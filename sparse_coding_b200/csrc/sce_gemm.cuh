@@ -43,13 +43,15 @@ struct GemmParams {
   EpiParams epi;
 };
 
-template <int BN, int BK, bool A_MN, bool B_MN, int STAGES>
+template <int BN, int BK, bool A_MN, bool B_MN, int STAGES, int EPI_WARP_BYTES = 0>
 struct GemmSmem {
   static constexpr int kATile = kBM * BK * 2;   // bytes, one of hi/lo
   static constexpr int kBTile = BN * BK * 2;
   static constexpr int kStage = 2 * kATile + 2 * kBTile;
   static constexpr int kBarOff = STAGES * kStage;
-  static constexpr int kBytes = kBarOff + 256 /*barriers + tmem ptr*/ + 1024 /*align slack*/;
+  static constexpr int kEpiOff = kBarOff + 256;  // barriers + tmem ptr live in the 256 bytes before
+  static constexpr int kBytes = kEpiOff + 4 * EPI_WARP_BYTES + 1024 /*align slack*/;
+  static_assert(kBytes <= 232448, "exceeds the 227 KB of shared memory one CTA may use");
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -62,7 +64,10 @@ gemm_split_kernel(const __grid_constant__ GemmParams<typename Epi::Params> p) {
   static_assert(BK % 16 == 0 && BK <= 64, "BK in {16,32,48,64}");
   static_assert(A_MN || BK == 64, "K-major A uses one 128-byte swizzled row per tile row: BK == 64");
   static_assert(B_MN || BK == 64, "K-major B uses one 128-byte swizzled row per tile row: BK == 64");
-  using SM = GemmSmem<BN, BK, A_MN, B_MN, STAGES>;
+  using SM = GemmSmem<BN, BK, A_MN, B_MN, STAGES, Epi::kWarpStageBytes>;
+  constexpr int EC = Epi::kCols;  // accumulator columns handed to the epilogue per call (32 or 64)
+  static_assert(EC == 32 || EC == 64, "epilogue chunk is 32 or 64 columns");
+  static_assert(BN % EC == 0, "tile width must be a multiple of the epilogue chunk");
   constexpr uint32_t kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
                                  : (2 * BN <= 256) ? 256 : 512;
 
@@ -235,23 +240,24 @@ gemm_split_kernel(const __grid_constant__ GemmParams<typename Epi::Params> p) {
       tc.col0 = tc.n_blk * BN;
       tc.warp_q = wq;
       tc.lane = lane;
-      Epi epi(p.epi, tc, p.m_total, p.n_total);
+      Epi epi(p.epi, tc, p.m_total, p.n_total, smem + SM::kEpiOff + wq * Epi::kWarpStageBytes);
 
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + uint32_t(acc * BN) + (uint32_t(wq * 32) << 16);
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld32(taddr + uint32_t(c * 32), r);
+      for (int c = 0; c < BN / EC; ++c) {
+        uint32_t r[EC];
+        tmem_ld32(taddr + uint32_t(c * EC), *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
+        if constexpr (EC == 64) tmem_ld32(taddr + uint32_t(c * EC + 32), *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
         tmem_ld_wait();
-        if (c == BN / 32 - 1) {
+        if (c == BN / EC - 1) {
           // all TMEM reads of this accumulator are done: hand it back to the MMA warp early
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&tempty_bar[acc]);
         }
-        epi.chunk(c * 32, r);
+        epi.chunk(c * EC, r);
       }
       epi.finish();
       if (++acc == 2) {
@@ -273,6 +279,8 @@ gemm_split_kernel(const __grid_constant__ GemmParams<typename Epi::Params> p) {
 // Epilogue: plain fp32 store  out[model][row][col] = acc   (dW tiles; self-test)
 // ------------------------------------------------------------------------------------------------
 struct EpiStoreF32 {
+  static constexpr int kCols = 32;
+  static constexpr int kWarpStageBytes = 0;
   struct Params {
     float* out;
     long long model_stride;  // elements
@@ -281,7 +289,7 @@ struct EpiStoreF32 {
   const Params& P;
   const TileCoord& T;
   int m_total, n_total;
-  __device__ EpiStoreF32(const Params& p, const TileCoord& t, int m, int n)
+  __device__ EpiStoreF32(const Params& p, const TileCoord& t, int m, int n, uint8_t*)
       : P(p), T(t), m_total(m), n_total(n) {}
   __device__ __forceinline__ void chunk(int c, const uint32_t (&r)[32]) {
     if (T.row >= m_total) return;

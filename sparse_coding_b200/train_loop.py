@@ -1,0 +1,258 @@
+"""The sweep's hot loop and its two neighbours: activation-chunk feeding and dictionary export.
+
+Reference behaviour being reproduced (HoagyC/sparse_coding @ 69c5ae0):
+  ensemble_train_loop           big_sweep.py:159-199   seeds, one step per sampler batch, optional wandb scalars
+  unstacked_to_learned_dicts    big_sweep.py:202-225   export [(LearnedDict, hyperparams)] per model
+  make_hyperparam_name          big_sweep.py:75-83     wandb key format
+  chunk loop / checkpoints      big_sweep.py:349-384, basic_l1_sweep.py:85-115
+
+What is B200-native here: the reference gathers every batch on the CPU (``dataset[batch_idxs]``, a 16 MiB fancy-index
+copy per step at config 2) and ships it through a pageable, synchronous H2D copy (its ``pin_memory()`` call discards
+the result). Here the whole chunk (2 GiB as fp16) is made resident in HBM once — staged through pinned
+memory on a side stream while the previous chunk is still training — and each batch is a device-side row gather
+(libsce ``sce_gather_rows``: fp16->fp32 conversion and optional mean-centring fused) followed by ``step_batch``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Iterable, List, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# naming (wandb keys) — big_sweep.py:75-83
+# ----------------------------------------------------------------------------------------------------------------
+def format_hyperparam_val(val) -> str:
+    return f"{val:.2E}".replace("+", "") if isinstance(val, float) else str(val)
+
+
+def make_hyperparam_name(setting: dict) -> str:
+    return "_".join(f"{k}_{format_hyperparam_val(v)}" for k, v in setting.items())
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# device-side batch gather
+# ----------------------------------------------------------------------------------------------------------------
+def gather_rows(chunk: torch.Tensor, idx: Optional[torch.Tensor], sub: Optional[torch.Tensor] = None,
+                out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[r] = float32(chunk[idx[r]]) - sub, on the GPU (chunk: CUDA fp16/fp32 [N,d]; idx: CUDA int64 [B])."""
+    if not chunk.is_cuda:
+        raise RuntimeError("gather_rows runs in the CUDA engine; the chunk must be resident on the GPU")
+    if chunk.dtype not in (torch.float16, torch.float32) or not chunk.is_contiguous():
+        raise TypeError("chunk must be a contiguous fp16 or fp32 tensor")
+    N, d = chunk.shape
+    B = N if idx is None else idx.numel()
+    if out is None:
+        out = torch.empty(B, d, dtype=torch.float32, device=chunk.device)
+    if idx is not None:
+        idx = idx.to(device=chunk.device, dtype=torch.int64).contiguous()
+    if sub is not None:
+        sub = sub.to(device=chunk.device, dtype=torch.float32).contiguous()
+    stream = C.c_void_p(torch.cuda.current_stream(chunk.device).cuda_stream)
+    with torch.cuda.device(chunk.device):
+        _lib.check(_lib.load().sce_gather_rows(chunk.data_ptr(), int(chunk.dtype == torch.float16), N, d,
+                                               idx.data_ptr() if idx is not None else None, B,
+                                               sub.data_ptr() if sub is not None else None, out.data_ptr(), stream),
+                   "sce_gather_rows")
+    return out
+
+
+def _batch_index_lists(sampler) -> Iterable[torch.Tensor]:
+    """Index tensors per batch. For the reference's ``BatchSampler(RandomSampler(range(N)), B, drop_last=False)``
+    (cluster_runs.py:28-32) the permutation is drawn in one go — the same numbers the reference would see, because
+    RandomSampler itself draws one ``torch.randperm`` per epoch — instead of building B-element Python lists."""
+    inner = getattr(sampler, "sampler", None)
+    bs = getattr(sampler, "batch_size", None)
+    if isinstance(sampler, torch.utils.data.BatchSampler) and isinstance(inner, torch.utils.data.RandomSampler) \
+            and not inner.replacement and inner.num_samples == len(inner.data_source):
+        perm = torch.tensor(list(iter(inner)), dtype=torch.int64)
+        n_full = len(perm) // bs * bs
+        for i in range(0, n_full, bs):
+            yield perm[i:i + bs]
+        if n_full < len(perm) and not sampler.drop_last:
+            yield perm[n_full:]
+        return
+    for idxs in sampler:
+        yield torch.as_tensor(idxs, dtype=torch.int64)
+
+
+def ensemble_train_loop(ensemble, cfg, args, ensemble_name, sampler, dataset, progress_counter):
+    """Drop-in for big_sweep.py:159-199. ``dataset`` is the chunk ([N,d], CPU or CUDA, fp16/fp32)."""
+    torch.set_grad_enabled(False)
+    torch.manual_seed(0)       # the reference re-seeds at every call: equal-length chunks get equal shuffles (Q7)
+    np.random.seed(0)
+    device = torch.device(args["device"])
+    use_wandb = bool(getattr(cfg, "use_wandb", False))
+    run = cfg.wandb_instance if use_wandb else None
+    chunk = dataset if dataset.is_cuda else dataset.to(device, non_blocking=True)
+    if not chunk.is_contiguous():
+        chunk = chunk.contiguous()
+    for i, batch_idxs in enumerate(_batch_index_lists(sampler)):
+        batch = gather_rows(chunk, batch_idxs.to(device, non_blocking=True))
+        losses, aux_buffer = ensemble.step_batch(batch)
+        if use_wandb:
+            num_nonzero = aux_buffer["c"].count_nonzero(dim=-1).float().mean(dim=-1)
+            host = {k: v.cpu() for k, v in losses.items()}            # one D2H per key, not one per model
+            nnz_host = num_nonzero.cpu()
+            log = {}
+            for m in range(ensemble.n_models):
+                hyperparam_values = {}
+                for ep in cfg.ensemble_hyperparams:
+                    if ep not in args:
+                        raise ValueError(f"Hyperparameter {ep} not found in args")
+                    hyperparam_values[ep] = args[ep]
+                for bp in cfg.buffer_hyperparams:
+                    if bp not in ensemble.buffers:
+                        raise ValueError(f"Hyperparameter {bp} not found in buffers")
+                    hyperparam_values[bp] = ensemble.buffers[bp][m].item()
+                name = make_hyperparam_name(hyperparam_values)
+                for k in host:
+                    log[f"{ensemble_name}_{name}_{k}"] = host[k][m].item()
+                log[f"{ensemble_name}_{name}_num_nonzero"] = nnz_host[m].item()
+            run.log(log, commit=True)
+        progress_counter.value = i
+
+
+def unstacked_to_learned_dicts(ensemble, args, ensemble_hyperparams, buffer_hyperparams):
+    """big_sweep.py:202-225: one (LearnedDict, {hyperparam: value}) per model, tensors on the CPU."""
+    learned_dicts = []
+    for params, buffers in ensemble.unstack(device="cpu"):
+        hyperparam_values = {}
+        for ep in ensemble_hyperparams:
+            if ep not in args:
+                raise ValueError(f"Hyperparameter {ep} not found in args")
+            hyperparam_values[ep] = args[ep]
+        for bp in buffer_hyperparams:
+            if bp not in buffers:
+                raise ValueError(f"Hyperparameter {bp} not found in buffers")
+            hyperparam_values[bp] = buffers[bp].item()
+        learned_dicts.append((ensemble.sig.to_learned_dict(params, buffers), hyperparam_values))
+    return learned_dicts
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# activation-chunk streaming: {folder}/{i}.pt  (fp16 [N,d], activation_dataset.py:499-503)
+# ----------------------------------------------------------------------------------------------------------------
+class ChunkStreamer:
+    """Iterates over device-resident chunks. While the caller trains on chunk i, chunk i+1 is read from disk into a
+    pinned staging buffer and copied to its own HBM buffer on a side stream (two device buffers, ping-pong)."""
+
+    def __init__(self, folder: str, order: Iterable[int], device, keep_dtype: bool = True):
+        self.folder, self.order, self.device = folder, list(order), torch.device(device)
+        self.keep_dtype = keep_dtype
+        self.copy_stream = torch.cuda.Stream(self.device)
+        self._pinned = None
+        self._dev = [None, None]
+
+    def _stage(self, slot: int, chunk_idx: int):
+        t = torch.load(os.path.join(self.folder, f"{chunk_idx}.pt"), map_location="cpu")
+        if not self.keep_dtype or t.dtype not in (torch.float16, torch.float32):
+            t = t.float()
+        t = t.contiguous()
+        if self._pinned is None or self._pinned.shape != t.shape or self._pinned.dtype != t.dtype:
+            self._pinned = torch.empty_like(t).pin_memory()
+        # the pinned buffer is reused: the previous async copy out of it must have finished
+        self.copy_stream.synchronize()
+        self._pinned.copy_(t)
+        if self._dev[slot] is None or self._dev[slot].shape != t.shape or self._dev[slot].dtype != t.dtype:
+            self._dev[slot] = torch.empty(t.shape, dtype=t.dtype, device=self.device)
+        with torch.cuda.stream(self.copy_stream):
+            self._dev[slot].copy_(self._pinned, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.copy_stream)
+        return ev
+
+    def __iter__(self):
+        if not self.order:
+            return
+        pending = self._stage(0, self.order[0])
+        for i, chunk_idx in enumerate(self.order):
+            slot = i & 1
+            torch.cuda.current_stream(self.device).wait_event(pending)
+            current = self._dev[slot]
+            if i + 1 < len(self.order):
+                # the other slot was last used two chunks ago; make the copy wait for the compute that read it
+                self.copy_stream.wait_stream(torch.cuda.current_stream(self.device))
+                pending = self._stage(slot ^ 1, self.order[i + 1])
+            yield chunk_idx, current
+
+
+class _Counter:
+    value = 0
+
+
+def train_on_chunks(ensemble, args: dict, dataset_folder: str, output_folder: str, batch_size: int,
+                    ensemble_hyperparams: List[str], buffer_hyperparams: List[str], n_repetitions: int = 1,
+                    center_activations: bool = False, cfg=None, chunk_order: Optional[List[int]] = None,
+                    save_schedule: str = "sweep"):
+    """The chunk loop of ``sweep`` (big_sweep.py:349-384) / ``basic_l1_sweep`` (basic_l1_sweep.py:85-115) for ONE
+    ensemble on ONE GPU, with streamed chunks. Writes ``_{i}/learned_dicts.pt`` (+ ``config.yaml`` when ``cfg`` is
+    given) on the reference's schedule: last chunk, or chunk count in {8, 16, …, 512}."""
+    import yaml
+
+    device = torch.device(args["device"])
+    n_chunks = len([f for f in os.listdir(dataset_folder) if f.endswith(".pt") and f[:-3].isdigit()])
+    if chunk_order is None:
+        chunk_order = list(np.random.permutation(n_chunks))
+        if n_repetitions is not None:
+            chunk_order = list(np.tile(chunk_order, n_repetitions))
+    os.makedirs(output_folder, exist_ok=True)
+    means = None
+    cfg = cfg if cfg is not None else type("Cfg", (), {"use_wandb": False})()
+    learned_dicts = []
+    for i, (chunk_idx, chunk) in enumerate(ChunkStreamer(dataset_folder, chunk_order, device)):
+        if center_activations:
+            if means is None:
+                means = chunk.float().mean(dim=0)
+                torch.save(means.cpu(), os.path.join(output_folder, "means.pt"))
+        N = chunk.shape[0]
+        sampler = torch.utils.data.BatchSampler(torch.utils.data.RandomSampler(range(N)), batch_size=batch_size,
+                                                drop_last=False)
+        torch.set_grad_enabled(False)
+        torch.manual_seed(0)
+        np.random.seed(0)
+        for j, idx in enumerate(_batch_index_lists(sampler)):
+            batch = gather_rows(chunk, idx.to(device, non_blocking=True), sub=means)
+            ensemble.step_batch(batch)
+        learned_dicts = unstacked_to_learned_dicts(ensemble, args, ensemble_hyperparams, buffer_hyperparams)
+        last = i == len(chunk_order) - 1
+        if last or (save_schedule == "sweep" and (i + 1) in [2 ** j for j in range(3, 10)]) or save_schedule == "every":
+            it_folder = os.path.join(output_folder, f"_{i}")
+            os.makedirs(it_folder, exist_ok=True)
+            torch.save(learned_dicts, os.path.join(it_folder, "learned_dicts.pt"))
+            if hasattr(cfg, "__dict__") or isinstance(cfg, dict):
+                try:
+                    with open(os.path.join(it_folder, "config.yaml"), "w") as f:
+                        yaml.dump({k: v for k, v in dict(vars(cfg) if not isinstance(cfg, dict) else cfg).items()
+                                   if isinstance(v, (int, float, str, bool, list, type(None)))}, f)
+                except Exception:
+                    pass
+    return learned_dicts
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# resume (the reference can only save dictionaries; Adam state is lost between runs — SURVEY.md §5)
+# ----------------------------------------------------------------------------------------------------------------
+def save_resume_state(ensemble, path: str) -> None:
+    sd = ensemble.state_dict()
+    cpu = lambda tree: {k: (cpu(v) if isinstance(v, dict) else v.detach().cpu()) for k, v in tree.items()}
+    torch.save({"params": cpu(sd["params"]), "buffers": cpu(sd["buffers"]), "optim_states": cpu(sd["optim_states"]),
+                "sig": sd["sig"], "optimizer_kwargs": sd["optimizer_kwargs"], "n_models": sd["n_models"],
+                "adam_count_mode": sd["adam_count_mode"], "fwd_passes": sd["fwd_passes"],
+                "bwd_passes": sd["bwd_passes"], "steps": sd["steps"], "no_stacking": sd["no_stacking"]}, path)
+
+
+def load_resume_state(path: str, device):
+    from .ensemble import FunctionalEnsemble
+    from .optim import adam
+    blob = torch.load(path, map_location="cpu", weights_only=False)
+    dev = lambda tree: {k: (dev(v) if isinstance(v, dict) else v.to(device)) for k, v in tree.items()}
+    sd = dict(blob)
+    sd.update(device=device, params=dev(blob["params"]), buffers=dev(blob["buffers"]),
+              optim_states=dev(blob["optim_states"]), optimizer_func=adam, materialize_code=False)
+    return FunctionalEnsemble.from_state(sd)
