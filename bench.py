@@ -63,7 +63,7 @@ def synth_batches(n_batches, B, d, seed, pin=False):
 
 
 class ClockSampler:
-    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    QUERY = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -75,12 +75,21 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.QUERY}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except OSError:
             self.proc = None
 
-    def stop(self):
+    @staticmethod
+    def _ts(text):
+        import datetime
+        try:
+            return datetime.datetime.strptime(text.strip(), "%Y/%m/%d %H:%M:%S.%f").timestamp()
+        except ValueError:
+            return None
+
+    def stop(self, t_begin=None, t_end=None):
+        """Samples are kept only if their timestamp lies inside [t_begin, t_end] (the timed region)."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -93,6 +102,9 @@ class ClockSampler:
         for line in open(self.path):
             f = [t.strip() for t in line.split(",")]
             if len(f) < 9:
+                continue
+            ts = self._ts(f[0])
+            if t_begin is not None and ts is not None and not (t_begin - 0.02 <= ts <= t_end + 0.02):
                 continue
             try:
                 sm.append(float(f[1]))
@@ -177,7 +189,7 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=60)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
@@ -220,25 +232,27 @@ def main():
         torch.cuda.synchronize()
 
     # ---------------- device-resident run: `value`
-    for i in range(W):
-        ens.step_batch(pool[i % n_pool])
-    barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for i in range(W):
+        ens.step_batch(pool[i % n_pool])
+    barrier()
     ens.profile_begin()
     launches = 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    t_begin = time.time()
     e0.record()
     for i in range(K):
         losses, aux = ens.step_batch(pool[i % n_pool])
         launches += ens.gpu_launches_last_call()
     e1.record()
     barrier()
+    t_end = time.time()
     ms = e0.elapsed_time(e1)
     phases = ens.profile_end()
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
     final_loss = losses["loss"].detach().clone()
 
     # ---------------- end-to-end run through the public API with host batches: `e2e`

@@ -132,9 +132,9 @@ static size_t carve(sce_plan* p, const sce_desc& d, uint8_t* base) {
   auto dwe = c.take<float>(M * n * dd);
   float* dwd = dwe;
   if (d.variant == SCE_UNTIED) dwd = c.take<float>(M * n * dd);
-  const size_t enc_parts = d.variant == SCE_TOPK ? B : tiles_mB * 4 * tiles_nN;
+  const size_t enc_parts = d.variant == SCE_TOPK ? B : tiles_mB * 8 * tiles_nN;
   auto pe = c.take<float>(M * enc_parts * 2);
-  auto pd = c.take<float>(M * tiles_mB * 4 * tiles_nD);
+  auto pd = c.take<float>(M * tiles_mB * 8 * tiles_nD);
   auto dbp = c.take<float>(M * tiles_mB * 4 * n);
   auto bn = c.take<float>(M);
   auto lob = c.take<float>(M);
@@ -360,7 +360,7 @@ static int run_pipeline(sce_plan* p, const float* x, int B, float* x_hat, bool b
     }
     if (rc) return rc;
     ++launches;
-    n_enc_parts = tiles_mB * 4 * ep.tiles_n;
+    n_enc_parts = tiles_mB * 8 * ep.tiles_n;
   } else {
     // scores -> fp32 (aliasing the dz pair), then per-row selection
     EpiStoreF32::Params sp;
@@ -420,7 +420,7 @@ static int run_pipeline(sce_plan* p, const float* x, int B, float* x_hat, bool b
     bias_norm_kernel<<<M, 256, 0, st>>>(p->b.encoder_bias, n, p->bnorm);
     ++launches;
   }
-  finalize_kernel<<<M, 256, 0, st>>>(p->part_enc, n_enc_parts, p->part_dec, tiles_mB * 4 * dp.tiles_n, p->b.l1_alpha,
+  finalize_kernel<<<M, 256, 0, st>>>(p->part_enc, n_enc_parts, p->part_dec, tiles_mB * 8 * dp.tiles_n, p->b.l1_alpha,
                                      p->b.encoder_bias ? p->b.bias_decay : nullptr, p->bnorm, B, dd, out_losses, out_nnz);
   ++launches;
   CUDA_TRY(cudaGetLastError());

@@ -31,50 +31,15 @@ __device__ __forceinline__ void store_bf16x32(__nv_bfloat16* dst, const uint32_t
 }
 
 // ------------------------------------------------------------------------------------------------
-// Warp-private staging tile: 32 rows x 64 bf16 (128 B per row, 4 KB), 16-byte chunks XOR-swizzled
-// by (row & 7) so that both the row-per-thread access (epilogue math) and the 8-lanes-per-row access
-// (coalesced 128-byte global lines) hit the 4-wavefront minimum of a 512-byte warp access.
+// (hi, lo) split of two fp32 values into packed bf16x2 words: one packed conversion per pair for hi
+// and one for lo (cvt.rn.bf16x2.f32), the residual formed on the fp32 pipe.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint4* stage_slot(uint8_t* buf, int row, int chunk) {
-  return reinterpret_cast<uint4*>(buf + row * 128 + ((chunk ^ (row & 7)) << 4));
-}
-// thread `lane` owns row `lane`: write its 64 bf16 (32 packed words)
-__device__ __forceinline__ void stage_put_row(uint8_t* buf, int lane, const uint32_t (&w)[32]) {
-#pragma unroll
-  for (int q = 0; q < 8; ++q) *stage_slot(buf, lane, q) = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
-}
-__device__ __forceinline__ void stage_get_row(uint8_t* buf, int lane, uint32_t (&w)[32]) {
-#pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    const uint4 v = *stage_slot(buf, lane, q);
-    w[4 * q] = v.x;
-    w[4 * q + 1] = v.y;
-    w[4 * q + 2] = v.z;
-    w[4 * q + 3] = v.w;
-  }
-}
-// staging tile -> global rows [row0, row0+32) x cols [col, col+64): 8 lanes write one 128-byte line
-__device__ __forceinline__ void stage_flush(uint8_t* buf, int lane, __nv_bfloat16* gbase /*row0, col*/, int ld,
-                                            int rows_valid, int cols_valid) {
-  const int q = lane & 7;
-#pragma unroll
-  for (int it = 0; it < 8; ++it) {
-    const int r = it * 4 + (lane >> 3);
-    if (r < rows_valid && q * 8 < cols_valid)
-      *reinterpret_cast<uint4*>(gbase + (long long)r * ld + q * 8) = *stage_slot(buf, r, q);
-  }
-}
-// global rows -> staging tile (same mapping)
-__device__ __forceinline__ void stage_fill(uint8_t* buf, int lane, const __nv_bfloat16* gbase, int ld,
-                                           int rows_valid, int cols_valid) {
-  const int q = lane & 7;
-#pragma unroll
-  for (int it = 0; it < 8; ++it) {
-    const int r = it * 4 + (lane >> 3);
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (r < rows_valid && q * 8 < cols_valid) v = *reinterpret_cast<const uint4*>(gbase + (long long)r * ld + q * 8);
-    *stage_slot(buf, r, q) = v;
-  }
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi2, uint32_t& lo2) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  hi2 = *reinterpret_cast<const uint32_t*>(&h);
+  const float ha = __uint_as_float(hi2 << 16), hb = __uint_as_float(hi2 & 0xFFFF0000u);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(a - ha, b - hb);
+  lo2 = *reinterpret_cast<const uint32_t*>(&l);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -83,14 +48,14 @@ __device__ __forceinline__ void stage_fill(uint8_t* buf, int lane, const __nv_bf
 // clamp(min=0)'s gradient of 1 at z == 0 without keeping z.
 // ------------------------------------------------------------------------------------------------
 struct EpiEncode {
-  static constexpr int kCols = 64;
-  static constexpr int kWarpStageBytes = 8192;  // hi tile + lo tile
+  static constexpr int kCols = 32;
+  static constexpr int kWarpStageBytes = 0;
   struct Params {
     const float* bias;             // [M, n] or nullptr
     const unsigned char* mask;     // [M, n] (1 = coefficient unused) or nullptr
     __nv_bfloat16* c_hi;           // [M, B, n]
     __nv_bfloat16* c_lo;
-    float* part;                   // [M][tiles_m*4][tiles_n][2]  (sum c, nnz)
+    float* part;                   // [M][tiles_m*8][tiles_n][2]  (sum c, nnz)
     long long c_model_stride;      // batch_max*n
     int ldc;                       // n
     int tiles_m, tiles_n;
@@ -99,50 +64,79 @@ struct EpiEncode {
   const Params& P;
   const TileCoord& T;
   int m_total, n_total;
-  uint8_t* stage;
-  float l1 = 0.f, nnz = 0.f;
-  __device__ EpiEncode(const Params& p, const TileCoord& t, int m, int n, uint8_t* st)
-      : P(p), T(t), m_total(m), n_total(n), stage(st) {}
+  float l1 = 0.f;
+  int nnz = 0;
+  __device__ EpiEncode(const Params& p, const TileCoord& t, int m, int n, uint8_t*)
+      : P(p), T(t), m_total(m), n_total(n) {}
 
-  __device__ __forceinline__ void chunk(int c, const uint32_t (&r)[64]) {
+  __device__ __forceinline__ void chunk(int c, const uint32_t (&r)[32]) {
     const int col = T.col0 + c;
     if (col >= n_total) return;  // warp-uniform
     const bool row_ok = T.row < m_total;
-    uint32_t whi[32], wlo[32];
+    uint32_t whi[16], wlo[16];
     const float* bias = P.bias ? P.bias + (long long)T.model * n_total + col : nullptr;
-    const unsigned char* mask = P.mask ? P.mask + (long long)T.model * n_total + col : nullptr;
+    float ls = 0.f;
+    int cnt = 0;
+    if (col + 32 <= n_total && !P.mask && bias) {
+      // fast path: whole chunk in range, no coefficient mask; bias fetched as 8 uniform float4
 #pragma unroll
-    for (int j = 0; j < 64; j += 2) {
-      __nv_bfloat16 h[2], l[2];
+      for (int j = 0; j < 32; j += 4) {
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + j));
+        const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const bool col_ok = col + j + u < n_total;
-        float z = __uint_as_float(r[j + u]) + ((bias && col_ok) ? __ldg(bias + j + u) : 0.f);
-        const bool masked = !col_ok || (mask && __ldg(mask + j + u));
-        float cv = (z > 0.f && !masked) ? z : 0.f;
-        split_bf16(cv, h[u], l[u]);
-        if (P.flag_zero && z == 0.f && !masked) h[u] = __ushort_as_bfloat16(0x8000);
-        if (row_ok) {
-          l1 += cv;
-          nnz += cv > 0.f ? 1.f : 0.f;
+        for (int u = 0; u < 4; u += 2) {
+          const float z0 = __uint_as_float(r[j + u]) + bb[u], z1 = __uint_as_float(r[j + u + 1]) + bb[u + 1];
+          const bool p0 = z0 > 0.f, p1 = z1 > 0.f;
+          const float c0 = p0 ? z0 : 0.f, c1 = p1 ? z1 : 0.f;
+          uint32_t h2, l2;
+          split2(c0, c1, h2, l2);
+          if (P.flag_zero) {
+            if (z0 == 0.f) h2 |= 0x00008000u;
+            if (z1 == 0.f) h2 |= 0x80000000u;
+          }
+          ls += c0 + c1;
+          cnt += int(p0) + int(p1);
+          whi[(j + u) >> 1] = h2;
+          wlo[(j + u) >> 1] = l2;
         }
       }
-      whi[j >> 1] = pack_bf16(h[0], h[1]);
-      wlo[j >> 1] = pack_bf16(l[0], l[1]);
+    } else {
+      const unsigned char* mask = P.mask ? P.mask + (long long)T.model * n_total + col : nullptr;
+#pragma unroll
+      for (int j = 0; j < 32; j += 2) {
+        float cv[2];
+        bool zf[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const bool col_ok = col + j + u < n_total;
+          const float z = __uint_as_float(r[j + u]) + ((bias && col_ok) ? __ldg(bias + j + u) : 0.f);
+          const bool masked = !col_ok || (mask && __ldg(mask + j + u));
+          cv[u] = (z > 0.f && !masked) ? z : 0.f;
+          zf[u] = P.flag_zero && z == 0.f && !masked;
+          ls += cv[u];
+          cnt += cv[u] > 0.f ? 1 : 0;
+        }
+        uint32_t h2, l2;
+        split2(cv[0], cv[1], h2, l2);
+        if (zf[0]) h2 |= 0x00008000u;
+        if (zf[1]) h2 |= 0x80000000u;
+        whi[j >> 1] = h2;
+        wlo[j >> 1] = l2;
+      }
     }
-    const int row0 = T.m_blk * kBM + T.warp_q * 32;
-    const long long off = (long long)T.model * P.c_model_stride + (long long)row0 * P.ldc + col;
-    __syncwarp();  // previous chunk's flush has finished reading the staging tiles
-    stage_put_row(stage, T.lane, whi);
-    stage_put_row(stage + 4096, T.lane, wlo);
-    __syncwarp();
-    stage_flush(stage, T.lane, P.c_hi + off, P.ldc, m_total - row0, n_total - col);
-    stage_flush(stage + 4096, T.lane, P.c_lo + off, P.ldc, m_total - row0, n_total - col);
+    if (row_ok) {
+      l1 += ls;
+      nnz += cnt;
+      const long long off = (long long)T.model * P.c_model_stride + (long long)T.row * P.ldc + col;
+      store_bf16x32(P.c_hi + off, whi, n_total - col);
+      store_bf16x32(P.c_lo + off, wlo, n_total - col);
+    }
   }
   __device__ __forceinline__ void finish() {
-    const float a = warp_sum(l1), b = warp_sum(nnz);
+    const float a = warp_sum(l1), b = warp_sum(float(nnz));
     if (T.lane == 0) {
-      float* o = P.part + ((((long long)T.model * P.tiles_m + T.m_blk) * 4 + T.warp_q) * P.tiles_n + T.n_blk) * 2;
+      float* o = P.part +
+                 ((((long long)T.model * P.tiles_m + T.m_blk) * 8 + T.grp * 4 + T.warp_q) * P.tiles_n + T.n_blk) * 2;
       o[0] = a;
       o[1] = b;
     }
@@ -161,7 +155,7 @@ struct EpiDecode {
     __nv_bfloat16* g_hi;           // [M, B, d]
     __nv_bfloat16* g_lo;
     float* x_hat;                  // optional [M, B, d] fp32 (evaluation / parity tests)
-    float* part;                   // [M][tiles_m*4][tiles_n]  (sum r^2)
+    float* part;                   // [M][tiles_m*8][tiles_n]  (sum r^2)
     long long g_model_stride;      // batch_max*d (workspace pitch)
     long long xhat_model_stride;   // B*d (caller's tensor)
     int ld;                        // d
@@ -184,19 +178,12 @@ struct EpiDecode {
     for (int j = 0; j < 32; j += 4) {
       float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
       const bool ok = col + j < n_total;  // d % 4 == 0
-      if (ok) xv = *reinterpret_cast<const float4*>(x + j);
-      const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
-      __nv_bfloat16 h[4], l[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const float rr = ok ? __uint_as_float(r[j + u]) - xs[u] : 0.f;
-        sq += rr * rr;
-        split_bf16(rr * P.gscale, h[u], l[u]);
-      }
-      whi[j >> 1] = pack_bf16(h[0], h[1]);
-      whi[(j >> 1) + 1] = pack_bf16(h[2], h[3]);
-      wlo[j >> 1] = pack_bf16(l[0], l[1]);
-      wlo[(j >> 1) + 1] = pack_bf16(l[2], l[3]);
+      if (ok) xv = __ldg(reinterpret_cast<const float4*>(x + j));
+      const float r0 = ok ? __uint_as_float(r[j]) - xv.x : 0.f, r1 = ok ? __uint_as_float(r[j + 1]) - xv.y : 0.f;
+      const float r2 = ok ? __uint_as_float(r[j + 2]) - xv.z : 0.f, r3 = ok ? __uint_as_float(r[j + 3]) - xv.w : 0.f;
+      sq += r0 * r0 + r1 * r1 + r2 * r2 + r3 * r3;
+      split2(r0 * P.gscale, r1 * P.gscale, whi[j >> 1], wlo[j >> 1]);
+      split2(r2 * P.gscale, r3 * P.gscale, whi[(j >> 1) + 1], wlo[(j >> 1) + 1]);
       if (P.x_hat && ok)
         *reinterpret_cast<float4*>(P.x_hat + (long long)T.model * P.xhat_model_stride + (long long)T.row * P.ld + col + j) =
             make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
@@ -208,7 +195,7 @@ struct EpiDecode {
   __device__ __forceinline__ void finish() {
     const float a = warp_sum(sq);
     if (T.lane == 0)
-      P.part[(((long long)T.model * P.tiles_m + T.m_blk) * 4 + T.warp_q) * P.tiles_n + T.n_blk] = a;
+      P.part[(((long long)T.model * P.tiles_m + T.m_blk) * 8 + T.grp * 4 + T.warp_q) * P.tiles_n + T.n_blk] = a;
   }
 };
 
@@ -217,8 +204,8 @@ struct EpiDecode {
 //         per-warp column sums of dz (32 rows) -> bias-gradient partials
 // ------------------------------------------------------------------------------------------------
 struct EpiDcode {
-  static constexpr int kCols = 64;
-  static constexpr int kWarpStageBytes = 8192;
+  static constexpr int kCols = 32;
+  static constexpr int kWarpStageBytes = 0;
   struct Params {
     const __nv_bfloat16* c_hi;     // [M, B, n]
     const float* l1_over_b;        // [M]: alpha_m / B
@@ -232,68 +219,59 @@ struct EpiDcode {
   const Params& P;
   const TileCoord& T;
   int m_total, n_total;
-  uint8_t* stage;
   float aB;
-  __device__ EpiDcode(const Params& p, const TileCoord& t, int m, int n, uint8_t* st)
-      : P(p), T(t), m_total(m), n_total(n), stage(st) {
+  __device__ EpiDcode(const Params& p, const TileCoord& t, int m, int n, uint8_t*)
+      : P(p), T(t), m_total(m), n_total(n) {
     aB = __ldg(P.l1_over_b + T.model);
   }
 
-  // 32 lanes x 32 columns -> lane j holds the sum of column j (31 shuffles)
-  __device__ __forceinline__ float transpose_reduce(float (&v)[32]) {
-#pragma unroll
-    for (int half = 16; half >= 1; half >>= 1) {
-      const bool upper = (T.lane & half) != 0;
-#pragma unroll
-      for (int i = 0; i < half; ++i) {
-        const float send = upper ? v[i] : v[i + half];
-        const float keep = upper ? v[i + half] : v[i];
-        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, half);
-      }
-    }
-    return v[0];
-  }
-
-  __device__ __forceinline__ void chunk(int c, const uint32_t (&r)[64]) {
+  __device__ __forceinline__ void chunk(int c, const uint32_t (&r)[32]) {
     const int col = T.col0 + c;
     if (col >= n_total) return;  // warp-uniform
-    const int row0 = T.m_blk * kBM + T.warp_q * 32;
-    const long long off = (long long)T.model * P.c_model_stride + (long long)row0 * P.ldc + col;
-    // the code tile (for the activity pattern), fetched with full 128-byte lines
-    uint32_t cw[32];
-    __syncwarp();
-    stage_fill(stage, T.lane, P.c_hi + off, P.ldc, m_total - row0, n_total - col);
-    __syncwarp();
-    stage_get_row(stage, T.lane, cw);
-    float dz0[32], dz1[32];
-    uint32_t whi[32], wlo[32];
+    const bool row_ok = T.row < m_total;
+    const long long off = (long long)T.model * P.c_model_stride + (long long)T.row * P.ldc + col;
+    uint32_t cw[16];
 #pragma unroll
-    for (int j = 0; j < 64; j += 2) {
-      __nv_bfloat16 h[2], l[2];
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const uint32_t bits = (cw[j >> 1] >> (16 * u)) & 0xFFFFu;
-        const bool pos = bits != 0u && !(bits & 0x8000u);   // c > 0
-        const bool gate = pos || bits == 0x8000u;           // z >= 0 (z == 0 flagged as -0.0)
-        const float v = gate ? __uint_as_float(r[j + u]) + (pos ? aB : 0.f) : 0.f;
-        if (j + u < 32) dz0[j + u] = v; else dz1[j + u - 32] = v;
-        split_bf16(v, h[u], l[u]);
-      }
-      whi[j >> 1] = pack_bf16(h[0], h[1]);
-      wlo[j >> 1] = pack_bf16(l[0], l[1]);
+    for (int j = 0; j < 4; ++j) {
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (row_ok && col + j * 8 < n_total) v = __ldg(reinterpret_cast<const uint4*>(P.c_hi + off + j * 8));
+      cw[4 * j] = v.x;
+      cw[4 * j + 1] = v.y;
+      cw[4 * j + 2] = v.z;
+      cw[4 * j + 3] = v.w;
     }
-    __syncwarp();  // everyone has read its code row
-    stage_put_row(stage, T.lane, whi);
-    stage_put_row(stage + 4096, T.lane, wlo);
-    __syncwarp();
-    stage_flush(stage, T.lane, P.dz_hi + off, P.ldc, m_total - row0, n_total - col);
-    stage_flush(stage + 4096, T.lane, P.dz_lo + off, P.ldc, m_total - row0, n_total - col);
+    float dz[32];
+    uint32_t whi[16], wlo[16];
+#pragma unroll
+    for (int j = 0; j < 32; j += 2) {
+      // bf16 bit patterns: 0x0001..0x7FFF positive (c > 0); 0x8000 is the "z == 0" flag written by encode
+      const uint32_t b0 = cw[j >> 1] & 0xFFFFu, b1 = cw[j >> 1] >> 16;
+      const bool pos0 = (b0 - 1u) < 0x7FFFu, pos1 = (b1 - 1u) < 0x7FFFu;
+      const bool gate0 = (b0 - 1u) < 0x8000u, gate1 = (b1 - 1u) < 0x8000u;
+      const float v0 = gate0 ? __uint_as_float(r[j]) + (pos0 ? aB : 0.f) : 0.f;
+      const float v1 = gate1 ? __uint_as_float(r[j + 1]) + (pos1 ? aB : 0.f) : 0.f;
+      dz[j] = v0;
+      dz[j + 1] = v1;
+      split2(v0, v1, whi[j >> 1], wlo[j >> 1]);
+    }
+    if (row_ok) {
+      store_bf16x32(P.dz_hi + off, whi, n_total - col);
+      store_bf16x32(P.dz_lo + off, wlo, n_total - col);
+    }
     if (P.db_part) {
-      float* o = P.db_part + (((long long)T.model * P.tiles_m + T.m_blk) * 4 + T.warp_q) * n_total + col;
-      const float s0 = transpose_reduce(dz0);
-      if (col + T.lane < n_total) o[T.lane] = s0;
-      const float s1 = transpose_reduce(dz1);
-      if (col + 32 + T.lane < n_total) o[32 + T.lane] = s1;
+      // transpose-reduce: 32 lanes x 32 columns -> lane j holds the sum of column j (31 shuffles)
+#pragma unroll
+      for (int half = 16; half >= 1; half >>= 1) {
+        const bool upper = (T.lane & half) != 0;
+#pragma unroll
+        for (int i = 0; i < half; ++i) {
+          const float send = upper ? dz[i] : dz[i + half];
+          const float keep = upper ? dz[i + half] : dz[i];
+          dz[i] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+        }
+      }
+      if (col + T.lane < n_total)
+        P.db_part[(((long long)T.model * P.tiles_m + T.m_blk) * 4 + T.warp_q) * n_total + col + T.lane] = dz[0];
     }
   }
   __device__ __forceinline__ void finish() {}

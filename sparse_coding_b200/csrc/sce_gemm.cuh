@@ -8,16 +8,20 @@
 // bf16 tensor pipe. Operands may be K-major (reduction index contiguous in HBM) or MN-major
 // (row/column index contiguous), so no transposed copies of activations/codes are ever written.
 //
-// One CTA per SM, 256 threads: warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM
-// allocator, warps 4..7 = epilogue (TMEM -> registers -> fused epilogue -> HBM). Accumulators are
+// One CTA per SM, 384 threads: warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM
+// allocator, warps 4..11 = epilogue (TMEM -> registers -> fused epilogue -> HBM). Accumulators are
 // double-buffered in TMEM so the epilogue of tile t overlaps the main loop of tile t+1.
+// Eight epilogue warps (two per TMEM lane quarter, alternating 32-column chunks) because a single
+// warp per scheduler is latency-bound: the r01a profile showed ~37 issued instructions per element
+// at IPC ~0.25 holding the tensor pipe at 31 % in the encode GEMM.
 #pragma once
 #include "sce_ptx.cuh"
 
 namespace sce {
 
 constexpr int kBM = 128;        // rows of the output tile == TMEM lanes
-constexpr int kGemmThreads = 256;
+constexpr int kGemmThreads = 384;
+constexpr int kEpiWarps = 8;
 constexpr int kMaxSets = 2;
 
 // What the epilogue functor sees for each tile.
@@ -28,6 +32,7 @@ struct TileCoord {
   int row;      // global output row owned by this thread (may be >= m_total: predicate!)
   int col0;     // first global output column of the tile
   int warp_q;   // epilogue warp quarter 0..3 (rows 32*warp_q .. +31 of the tile)
+  int grp;      // epilogue warp group 0..1 (handles the 32-column chunks with chunk % 2 == grp)
   int lane;
 };
 
@@ -103,7 +108,7 @@ gemm_split_kernel(const __grid_constant__ GemmParams<typename Epi::Params> p) {
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 4);
+      mbar_init(&tempty_bar[s], kEpiWarps);
     }
     fence_mbar_init();
   }
@@ -228,6 +233,7 @@ gemm_split_kernel(const __grid_constant__ GemmParams<typename Epi::Params> p) {
   } else if (warp >= 4) {
     // ======================= epilogue =======================
     const int wq = warp & 3;
+    const int grp = (warp - 4) >> 2;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -239,19 +245,22 @@ gemm_split_kernel(const __grid_constant__ GemmParams<typename Epi::Params> p) {
       tc.row = tc.m_blk * kBM + wq * 32 + lane;
       tc.col0 = tc.n_blk * BN;
       tc.warp_q = wq;
+      tc.grp = grp;
       tc.lane = lane;
       Epi epi(p.epi, tc, p.m_total, p.n_total, smem + SM::kEpiOff + wq * Epi::kWarpStageBytes);
 
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + uint32_t(acc * BN) + (uint32_t(wq * 32) << 16);
+      constexpr int kChunks = BN / EC;
+      static_assert(kChunks % 2 == 0, "the two epilogue warp groups alternate chunks");
 #pragma unroll 1
-      for (int c = 0; c < BN / EC; ++c) {
+      for (int c = grp; c < kChunks; c += 2) {
         uint32_t r[EC];
         tmem_ld32(taddr + uint32_t(c * EC), *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
         if constexpr (EC == 64) tmem_ld32(taddr + uint32_t(c * EC + 32), *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
         tmem_ld_wait();
-        if (c == BN / EC - 1) {
+        if (c + 2 >= kChunks) {
           // all TMEM reads of this accumulator are done: hand it back to the MMA warp early
           tc_fence_before();
           __syncwarp();
