@@ -1,0 +1,198 @@
+"""CPU-side tests (no GPU): the C-ABI library loads and exports every symbol include/sce.h declares, argument
+validation across the ABI, the host-side mirror of the reference interface (stacking, state_dict, optimiser
+resolution, export types, checkpoint pickle names, wandb key format), and the loud failure when asked to compute
+without CUDA."""
+import ctypes as C
+import io
+import os
+import pickle
+import re
+
+import pytest
+import torch
+
+import sparse_coding_b200 as S
+from sparse_coding_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "sce.h")).read()
+    declared = set(re.findall(r"\b(sce_[a-z_]+)\s*\(", header))
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.sce_version() == 100
+
+
+def test_abi_validation_without_device():
+    lib = _lib.load()
+    desc = _lib.SceDesc(variant=0, n_models=2, d=64, n=128, batch_max=256, x_per_model=0, lr=1e-3, beta1=0.9,
+                        beta2=0.999, eps=1e-8, eps_root=0.0, adam_count_mode=0, fwd_passes=3, bwd_passes=3,
+                        norm_floor=1e-8)
+    need = lib.sce_workspace_bytes(C.byref(desc))
+    assert need > 0 and need % 1024 == 0
+    desc.batch_max = 512
+    assert lib.sce_workspace_bytes(C.byref(desc)) > need          # grows with the batch
+    desc.d = 63                                                      # not a multiple of 8
+    assert lib.sce_workspace_bytes(C.byref(desc)) == 0
+    assert b"multiples of 8" in lib.sce_last_error()
+    desc.d = 64
+    desc.fwd_passes = 2
+    assert lib.sce_workspace_bytes(C.byref(desc)) == 0
+    plan = C.c_void_p()
+    desc.fwd_passes = 3
+    bufs = _lib.SceBuffers()                                         # all NULL
+    assert lib.sce_plan_create(C.byref(desc), C.byref(bufs), C.byref(plan)) == -1
+    assert b"required" in lib.sce_last_error()
+    assert lib.sce_plan_destroy(None) == 0
+    assert lib.sce_step(None, None, 1, None, None, None) == -1
+
+
+def test_workspace_size_config2():
+    """Config 2 (M=16, d=512, n=4096, B=8192): the (hi, lo) bf16 code + code gradient dominate: 4 x 1 GiB."""
+    lib = _lib.load()
+    desc = _lib.SceDesc(variant=0, n_models=16, d=512, n=4096, batch_max=8192, x_per_model=0, lr=1e-3, beta1=0.9,
+                        beta2=0.999, eps=1e-8, eps_root=0.0, adam_count_mode=0, fwd_passes=3, bwd_passes=3,
+                        norm_floor=1e-8)
+    need = lib.sce_workspace_bytes(C.byref(desc))
+    assert 4.5 * 2**30 < need < 5.5 * 2**30
+
+
+def test_no_cpu_fallback():
+    models = [S.FunctionalTiedSAE.init(16, 32, 1e-3) for _ in range(2)]
+    ens = S.FunctionalEnsemble(models, S.FunctionalTiedSAE, S.adam, {"lr": 1e-3}, device="cpu")
+    with pytest.raises(RuntimeError, match="no CPU implementation"):
+        ens.step_batch(torch.randn(8, 16))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        S.FunctionalTiedSAE.loss(*models[0], torch.randn(8, 16))
+
+    class Custom(S.DictSignature):
+        pass
+
+    with pytest.raises(NotImplementedError, match="no engine variant"):
+        S.FunctionalEnsemble(models, Custom, S.adam, {"lr": 1e-3}, device="cpu")
+
+
+def test_init_matches_reference_initialisers():
+    """Same RNG consumption as the reference's init (xavier encoder, zero bias, [decoder]) => identical tensors
+    to the golden fixtures' parameters for the same seed (tests/golden/tied_small.pt was made with seed 0)."""
+    fx = torch.load(os.path.join(ROOT, "tests", "golden", "tied_small.pt"), weights_only=False)
+    torch.manual_seed(0)
+    for i, l1 in enumerate([1e-3, 3e-3, 1e-2]):
+        p, b = S.FunctionalTiedSAE.init(32, 64, l1, dtype=torch.float32)
+        assert torch.equal(p["encoder"], fx["params"]["encoder"][i])
+        assert torch.equal(p["encoder_bias"], fx["params"]["encoder_bias"][i])
+        assert float(b["l1_alpha"]) == pytest.approx(l1)
+        assert set(b) == {"center_rot", "center_trans", "center_scale", "l1_alpha", "bias_decay"}
+    p, b = S.FunctionalSAE.init(8, 16, 1e-3, bias_decay=0.5)
+    assert set(p) == {"encoder", "encoder_bias", "decoder"} and float(b["bias_decay"]) == 0.5
+    p, b = S.FunctionalMaskedTiedSAE.init(8, 16, 32, 1e-3)
+    assert p["encoder"].shape == (32, 8) and int(b["dict_size"]) == 16
+    assert b["coef_mask"].tolist() == [False] * 16 + [True] * 16
+    p, b = S.TopKEncoder.init(8, 16, 4)
+    assert set(p) == {"dict"} and b["sparsity"].dtype == torch.long
+
+
+def test_stack_unstack_state_dict_roundtrip():
+    models = [S.FunctionalSAE.init(8, 16, a, bias_decay=0.1 * i) for i, a in enumerate((1e-3, 1e-2, 1e-1))]
+    ens = S.FunctionalEnsemble(models, S.FunctionalSAE, "adam", {"lr": 3e-4}, device="cpu")
+    assert ens.n_models == 3 and ens.params["encoder"].shape == (3, 16, 8)
+    assert ens.buffers["l1_alpha"].shape == (3,)
+    assert ens.optimizer.lr == pytest.approx(3e-4)
+    back = ens.unstack(device="cpu")
+    for (p0, b0), (p1, b1) in zip(models, back):
+        assert all(torch.equal(p0[k], p1[k]) for k in p0) and all(torch.equal(b0[k], b1[k]) for k in b0)
+    sd = ens.state_dict()
+    for key in ("device", "n_models", "params", "buffers", "sig", "no_stacking", "optimizer_func", "optimizer_kwargs",
+                "optim_states"):                                   # the reference's keys (ensemble.py:150-161)
+        assert key in sd
+    blob = io.BytesIO()
+    torch.save(sd, blob)                                            # must survive pickling (mp spawn)
+    blob.seek(0)
+    ens2 = S.FunctionalEnsemble.from_state(torch.load(blob, weights_only=False))
+    assert torch.equal(ens2.params["decoder"], ens.params["decoder"]) and ens2.sig is S.FunctionalSAE
+    ens.to_shared_memory()
+    assert ens.params["encoder"].is_shared()
+
+
+def test_optimizer_resolution():
+    from sparse_coding_b200.optim import resolve_optimizer
+    assert resolve_optimizer("adam", {"lr": 1e-2}).lr == pytest.approx(1e-2)
+    cfg = resolve_optimizer(S.adam, {"lr": 1e-3, "betas": (0.8, 0.9), "eps": 1e-6})
+    assert (cfg.b1, cfg.b2, cfg.eps) == (pytest.approx(0.8), pytest.approx(0.9), pytest.approx(1e-6))
+    with pytest.raises(ValueError):
+        resolve_optimizer("sgd", {"lr": 1e-3})
+    with pytest.raises(NotImplementedError):
+        S.adam(lr=1e-3, weight_decay=0.1)
+    with pytest.raises(ValueError):
+        S.optim_str_to_func("sgd")
+    assert S.optim_str_to_func("adam") is S.adam
+
+
+def test_learned_dicts_match_reference(golden):
+    fx = golden("learned_dicts")
+    tied = S.TiedSAE(fx["encoder"], fx["bias"], centering=(fx["trans"], fx["rot"], fx["scale"]), norm_encoder=True)
+    untied = S.UntiedSAE(fx["encoder"], fx["decoder"], fx["bias"])
+    tk = S.TopKLearnedDict(fx["decoder"] / fx["decoder"].norm(dim=-1, keepdim=True), fx["topk_k"])
+    X = fx["batch"]
+    tol = dict(rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(tied.encode(tied.center(X)), fx["tied_encode"], **tol)
+    torch.testing.assert_close(tied.predict(X), fx["tied_predict"], **tol)
+    torch.testing.assert_close(tied.get_learned_dict(), fx["tied_dict"], **tol)
+    torch.testing.assert_close(untied.encode(X), fx["untied_encode"], **tol)
+    torch.testing.assert_close(untied.predict(X), fx["untied_predict"], **tol)
+    torch.testing.assert_close(untied.get_learned_dict(), fx["untied_dict"], **tol)
+    torch.testing.assert_close(tk.encode(X), fx["topk_encode"], **tol)
+    torch.testing.assert_close(tk.predict(X), fx["topk_predict"], **tol)
+    assert (tied.n_feats, tied.activation_size) == (64, 32) and tied.n_dict_components() == 64
+    torch.testing.assert_close(tied.uncenter(tied.center(X)), X, rtol=1e-4, atol=1e-5)
+
+
+def test_checkpoint_pickles_use_reference_names(tmp_path):
+    """learned_dicts.pt written here must resolve inside the reference repo: classes pickle as
+    autoencoders.learned_dict.* / autoencoders.topk_encoder.* (big_sweep.py:378-384 layout)."""
+    from sparse_coding_b200.train_loop import unstacked_to_learned_dicts
+    models = [S.FunctionalTiedSAE.init(8, 16, a) for a in (1e-3, 1e-2)]
+    ens = S.FunctionalEnsemble(models, S.FunctionalTiedSAE, S.adam, {"lr": 1e-3}, device="cpu")
+    dicts = unstacked_to_learned_dicts(ens, {"dict_size": 16, "device": "cpu"}, ["dict_size"], ["l1_alpha"])
+    assert [h["dict_size"] for _, h in dicts] == [16, 16]
+    assert dicts[1][1]["l1_alpha"] == pytest.approx(1e-2)
+    path = tmp_path / "learned_dicts.pt"
+    torch.save(dicts, path)
+    raw = open(path, "rb").read()
+    assert b"autoencoders.learned_dict" in raw and b"sparse_coding_b200" not in raw
+    loaded = torch.load(path, weights_only=False)
+    ld, hp = loaded[0]
+    assert type(ld).__name__ == "TiedSAE" and ld.norm_encoder and ld.encoder.shape == (16, 8)
+    import autoencoders.learned_dict as shim
+    assert isinstance(ld, shim.TiedSAE)
+    tk = S.TopKEncoder.to_learned_dict(*S.TopKEncoder.init(8, 16, 3))
+    assert b"autoencoders.topk_encoder" in pickle.dumps(tk)
+    with pytest.raises(ValueError, match="not found in args"):
+        unstacked_to_learned_dicts(ens, {}, ["dict_size"], [])
+
+
+def test_hyperparam_names():
+    from sparse_coding_b200.train_loop import format_hyperparam_val, make_hyperparam_name
+    assert format_hyperparam_val(1e-3) == "1.00E-03"
+    assert format_hyperparam_val(2048.0) == "2.05E03"
+    assert format_hyperparam_val(4096) == "4096"
+    assert make_hyperparam_name({"dict_size": 4096, "l1_alpha": 3e-4}) == "dict_size_4096_l1_alpha_3.00E-04"
+
+
+def test_batch_index_lists_follow_the_reference_sampler():
+    """The one-shot permutation must be exactly what BatchSampler(RandomSampler) yields batch by batch."""
+    from sparse_coding_b200.train_loop import _batch_index_lists
+    N, B = 1000, 128
+    mk = lambda: torch.utils.data.BatchSampler(torch.utils.data.RandomSampler(range(N)), batch_size=B, drop_last=False)
+    torch.manual_seed(0)
+    ref = [list(b) for b in mk()]
+    torch.manual_seed(0)
+    got = [t.tolist() for t in _batch_index_lists(mk())]
+    assert got == ref and len(got[-1]) == N - (N // B) * B
+    torch.manual_seed(0)
+    again = [t.tolist() for t in _batch_index_lists(mk())]
+    assert again == ref                                             # Q7: same shuffle after re-seeding
