@@ -1,0 +1,176 @@
+"""GPU tests of the callers either side of the step: device-side batch gather, the drop-in
+``ensemble_train_loop``, chunk streaming + checkpoint layout, resume, per-model batches, the host-fed C-ABI step."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import sae_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def relnorm(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).norm() / b.norm().clamp(min=1e-30))
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.float32])
+def test_gather_rows_bit_exact(dtype):
+    """out[r] = float32(chunk[idx[r]]) - sub is pure data movement + one subtraction: bit-exact vs torch."""
+    from sparse_coding_b200.train_loop import gather_rows
+    gen = torch.Generator().manual_seed(0)
+    chunk = torch.randn(5000, 192, generator=gen).to(dtype)
+    idx = torch.randint(0, 5000, (777,), generator=gen)
+    sub = torch.randn(192, generator=gen)
+    dev = chunk.cuda()
+    assert torch.equal(gather_rows(dev, idx.cuda()).cpu(), chunk[idx].float())
+    assert torch.equal(gather_rows(dev, idx.cuda(), sub=sub.cuda()).cpu(), chunk[idx].float() - sub)
+    assert torch.equal(gather_rows(dev, None).cpu(), chunk.float())
+    assert gather_rows(dev, idx[:1].cuda()).shape == (1, 192)
+
+
+def _clone(ms):
+    return [({k: v.clone() for k, v in p.items()}, {k: v.clone() for k, v in b.items()}) for p, b in ms]
+
+
+def test_ensemble_train_loop_matches_reference_loop():
+    """big_sweep.py:159-199 semantics on one chunk: same seeds, same sampler, same batches (incl. the short last
+    one) as the restated reference loop; final parameters agree with the oracle trained on the same batches."""
+    import sparse_coding_b200 as S
+    from sparse_coding_b200.train_loop import ensemble_train_loop
+    torch.manual_seed(0)
+    d, n, N, B = 64, 128, 1000, 256
+    models = [S.FunctionalTiedSAE.init(d, n, a) for a in (1e-3, 1e-2)]
+    chunk = torch.randn(N, d, generator=torch.Generator().manual_seed(5)).half()      # chunks are fp16 on disk
+    ens = S.FunctionalEnsemble(_clone(models), S.FunctionalTiedSAE, S.adam, {"lr": 1e-3}, device="cuda")
+    ref = O.RefPortEnsemble(_clone(models), O.SIG_LOSSES["tied"], lr=1e-3)
+
+    class Cfg:
+        use_wandb = False
+
+    class Counter:
+        value = -1
+
+    mk = lambda: torch.utils.data.BatchSampler(torch.utils.data.RandomSampler(range(N)), batch_size=B, drop_last=False)
+    ctr = Counter()
+    ensemble_train_loop(ens, Cfg(), {"device": "cuda", "batch_size": B}, "ens", mk(), chunk, ctr)
+    assert ctr.value == 3                                     # 4 batches: 256, 256, 256, 232
+    torch.manual_seed(0)                                      # what the reference loop does at entry
+    np.random.seed(0)
+    data = chunk.float()
+    for idxs in mk():
+        ref.step_batch(data[idxs])
+    assert relnorm(ens.params["encoder"], ref.params["encoder"]) <= 1e-3
+    assert relnorm(ens.params["encoder_bias"], ref.params["encoder_bias"]) <= 1e-3 + 1e-9
+
+
+def test_wandb_logging_keys():
+    import sparse_coding_b200 as S
+    from sparse_coding_b200.train_loop import ensemble_train_loop
+    logs = []
+
+    class Run:
+        def log(self, d, commit=True):
+            logs.append(d)
+
+    class Cfg:
+        use_wandb = True
+        wandb_instance = Run()
+        ensemble_hyperparams = ["dict_size"]
+        buffer_hyperparams = ["l1_alpha"]
+
+    class Counter:
+        value = 0
+
+    torch.manual_seed(0)
+    models = [S.FunctionalTiedSAE.init(32, 64, a) for a in (1e-3, 1e-2)]
+    ens = S.FunctionalEnsemble(models, S.FunctionalTiedSAE, S.adam, {"lr": 1e-3}, device="cuda")
+    sampler = torch.utils.data.BatchSampler(torch.utils.data.SequentialSampler(range(128)), batch_size=64, drop_last=False)
+    ensemble_train_loop(ens, Cfg(), {"device": "cuda", "dict_size": 64}, "e0", sampler, torch.randn(128, 32), Counter())
+    assert len(logs) == 2
+    keys = set(logs[0])
+    for l1 in ("1.00E-03", "1.00E-02"):
+        for k in ("loss", "l_reconstruction", "l_l1", "num_nonzero"):
+            assert f"e0_dict_size_64_l1_alpha_{l1}_{k}" in keys
+    assert all(isinstance(v, float) for v in logs[0].values())
+
+
+def test_chunk_streaming_checkpoints_and_resume(tmp_path):
+    """{i}.pt fp16 chunks -> streamed training -> `_{i}/learned_dicts.pt` in the reference's pickle layout; a
+    resumed ensemble (params + Adam moments + step count) continues bit-identically."""
+    import sparse_coding_b200 as S
+    from sparse_coding_b200.train_loop import load_resume_state, save_resume_state, train_on_chunks
+    data = tmp_path / "data"
+    out = tmp_path / "out"
+    data.mkdir()
+    gen = torch.Generator().manual_seed(0)
+    for i in range(3):
+        torch.save(torch.randn(700, 64, generator=gen).half(), data / f"{i}.pt")
+    torch.manual_seed(1)
+    models = [S.FunctionalTiedSAE.init(64, 128, a) for a in (1e-3, 1e-2)]
+    args = {"device": "cuda", "dict_size": 128, "batch_size": 256}
+    mk = lambda: S.FunctionalEnsemble(_clone(models), S.FunctionalTiedSAE, S.adam, {"lr": 1e-3}, device="cuda",
+                                      adam_count_mode="standard")
+    ens = mk()
+    dicts = train_on_chunks(ens, args, str(data), str(out), 256, ["dict_size"], ["l1_alpha"], chunk_order=[0, 1, 2],
+                            center_activations=True)
+    assert os.path.exists(out / "_2" / "learned_dicts.pt") and os.path.exists(out / "means.pt")
+    loaded = torch.load(out / "_2" / "learned_dicts.pt", weights_only=False)
+    assert len(loaded) == 2 and type(loaded[0][0]).__module__ == "autoencoders.learned_dict"
+    assert loaded[1][1] == {"dict_size": 128, "l1_alpha": pytest.approx(1e-2)}
+    torch.testing.assert_close(loaded[0][0].encoder, ens.params["encoder"][0].cpu())
+    x = torch.randn(16, 64)
+    assert loaded[0][0].predict(x).shape == (16, 64)
+    # --- resume: train 2 chunks, save, reload, train the third == training 3 chunks in one go
+    ens_a = mk()
+    train_on_chunks(ens_a, args, str(data), str(tmp_path / "o2"), 256, ["dict_size"], ["l1_alpha"], chunk_order=[0, 1])
+    save_resume_state(ens_a, str(tmp_path / "resume.pt"))
+    ens_b = load_resume_state(str(tmp_path / "resume.pt"), "cuda")
+    assert ens_b._steps == 6 and ens_b.adam_count_mode == "standard"
+    train_on_chunks(ens_b, args, str(data), str(tmp_path / "o3"), 256, ["dict_size"], ["l1_alpha"], chunk_order=[2])
+    ens_c = mk()
+    train_on_chunks(ens_c, args, str(data), str(tmp_path / "o4"), 256, ["dict_size"], ["l1_alpha"], chunk_order=[0, 1, 2])
+    assert torch.equal(ens_b.params["encoder"], ens_c.params["encoder"])
+    assert torch.equal(ens_b.optim_states["nu"]["encoder"], ens_c.optim_states["nu"]["encoder"])
+
+
+def test_per_model_batches_expand_dims_false():
+    """step_batch(x, expand_dims=False) with x [M,B,d] (ensemble.py:177-178): every model sees its own batch."""
+    import sparse_coding_b200 as S
+    torch.manual_seed(0)
+    d, n, B = 64, 128, 96
+    models = [S.FunctionalSAE.init(d, n, a) for a in (1e-3, 1e-2, 3e-2)]
+    ens = S.FunctionalEnsemble(_clone(models), S.FunctionalSAE, S.adam, {"lr": 1e-3}, device="cuda")
+    X = torch.randn(3, B, d)
+    grads, (loss, aux) = ens.grads_batch(X.cuda(), expand_dims=False)
+    for i, (p, b) in enumerate(models):
+        f = O.untied_grads(p["encoder"].double(), p["encoder_bias"].double(), p["decoder"].double(), X[i].double(),
+                           float(b["l1_alpha"]))
+        assert abs(float(loss["loss"][i]) - float(f["loss"])) <= 1e-4 * float(f["loss"])
+        assert relnorm(grads["decoder"][i], f["grads"]["decoder"]) <= 2e-4
+        assert relnorm(grads["encoder"][i], f["grads"]["encoder"]) <= 2e-4
+
+
+def test_host_fed_step_through_c_abi():
+    """sce_step_host: HOST batch in, HOST losses out (the e2e path of bench.py), identical to the device path."""
+    import sparse_coding_b200 as S
+    from sparse_coding_b200 import _lib
+    torch.manual_seed(0)
+    d, n, B = 64, 128, 200
+    models = [S.FunctionalTiedSAE.init(d, n, a) for a in (1e-3, 1e-2)]
+    ens_a = S.FunctionalEnsemble(_clone(models), S.FunctionalTiedSAE, S.adam, {"lr": 1e-3}, device="cuda")
+    ens_b = S.FunctionalEnsemble(_clone(models), S.FunctionalTiedSAE, S.adam, {"lr": 1e-3}, device="cuda")
+    X = torch.randn(B, d).pin_memory()
+    la, _ = ens_a.step_batch(X.cuda())
+    ens_b.forward_batch(X.cuda())                       # builds the plan
+    losses = torch.empty(2, 4).pin_memory()
+    nnz = torch.empty(2).pin_memory()
+    lib = _lib.load()
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    _lib.check(lib.sce_step_host(ens_b._plan, X.data_ptr(), B, losses.data_ptr(), nnz.data_ptr(), stream), "sce_step_host")
+    assert torch.equal(losses[:, 0], la["loss"].cpu())
+    assert torch.equal(ens_a.params["encoder"], ens_b.params["encoder"])
+    assert lib.sce_get_step_count(ens_b._plan) == 1
