@@ -48,6 +48,7 @@ struct GemmMaps {  // tensor maps of one GEMM for one batch size
 };
 struct BatchMaps {
   GemmMaps encode, decode, dcode, dw_enc, dw_dec;
+  CUtensorMap st_c_hi, st_c_lo, st_dz_hi, st_dz_lo;  // epilogue TMA-store maps
 };
 
 struct sce_plan {
@@ -220,6 +221,10 @@ static int build_maps(sce_plan* p, int B, BatchMaps** out) {
     ok &= act(&m->dw_enc.a_hi[1], &m->dw_enc.a_lo[1], p->c_hi, p->c_lo, M, n, kBkDw);
     ok &= act(&m->dw_enc.b_hi[1], &m->dw_enc.b_lo[1], p->g_hi, p->g_lo, M, dd, kBkDw);
   }
+  ok &= make_tmap_bf16_store32(&m->st_c_hi, p->c_hi, M, (uint64_t)B, n, Bm * n);
+  ok &= make_tmap_bf16_store32(&m->st_c_lo, p->c_lo, M, (uint64_t)B, n, Bm * n);
+  ok &= make_tmap_bf16_store32(&m->st_dz_hi, p->dz_hi, M, (uint64_t)B, n, Bm * n);
+  ok &= make_tmap_bf16_store32(&m->st_dz_lo, p->dz_lo, M, (uint64_t)B, n, Bm * n);
   if (!ok) {
     delete m;
     return fail(SCE_ERR_CUDA, "cuTensorMapEncodeTiled failed (B=%d, M=%d, n=%d, d=%d)", B, d.n_models, d.n, d.d);
@@ -342,6 +347,8 @@ static int run_pipeline(sce_plan* p, const float* x, int B, float* x_hat, bool b
   int n_enc_parts;
   if (d.variant != SCE_TOPK) {
     EpiEncode::Params ep;
+    ep.out_hi = maps->st_c_hi;
+    ep.out_lo = maps->st_c_lo;
     ep.bias = p->b.encoder_bias;
     ep.mask = p->b.coef_mask;
     ep.c_hi = p->c_hi;
@@ -429,6 +436,8 @@ static int run_pipeline(sce_plan* p, const float* x, int B, float* x_hat, bool b
   if (backward) {
     // ---- dcode
     EpiDcode::Params zp;
+    zp.out_hi = maps->st_dz_hi;
+    zp.out_lo = maps->st_dz_lo;
     zp.c_hi = p->c_hi;
     zp.l1_over_b = p->l1_over_b;
     zp.dz_hi = p->dz_hi;

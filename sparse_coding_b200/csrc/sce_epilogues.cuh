@@ -31,6 +31,37 @@ __device__ __forceinline__ void store_bf16x32(__nv_bfloat16* dst, const uint32_t
 }
 
 // ------------------------------------------------------------------------------------------------
+// Epilogue output staging: each epilogue warp owns two 2 KB shared-memory tiles (hi, lo) of 32 rows x
+// 32 bf16 (64-byte rows, TMA 64-byte swizzle: 16-byte chunk index ^= (row >> 1) & 3). A thread writes its
+// own row with four conflict-free 16-byte stores; one lane then hands the tile to the TMA engine, which
+// writes full lines to HBM and clips rows/columns outside the tensor. Replaces 32-line scattered STG.128
+// (the r01b profile had the encode/dcode epilogues bound by L1 line requests, ~16 k per tile).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void stage_row32(uint8_t* tile, int lane, const uint32_t (&w)[16]) {
+  const int sw = (lane >> 1) & 3;
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+    *reinterpret_cast<uint4*>(tile + lane * 64 + ((q ^ sw) << 4)) =
+        make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+}
+// whole warp: wait until the previous tile pair has been read out, write the new one, launch its stores
+__device__ __forceinline__ void stage_and_store(uint8_t* stage, int lane, const uint32_t (&whi)[16],
+                                                const uint32_t (&wlo)[16], const CUtensorMap* m_hi,
+                                                const CUtensorMap* m_lo, int col, int row0, int model) {
+  if (lane == 0) tma_store_wait_read();
+  __syncwarp();
+  stage_row32(stage, lane, whi);
+  stage_row32(stage + 2048, lane, wlo);
+  fence_proxy_async_smem();
+  __syncwarp();
+  if (lane == 0) {
+    tma_store_3d(m_hi, stage, col, row0, model);
+    tma_store_3d(m_lo, stage + 2048, col, row0, model);
+    tma_store_commit();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // (hi, lo) split of two fp32 values into packed bf16x2 words: one packed conversion per pair for hi
 // and one for lo (cvt.rn.bf16x2.f32), the residual formed on the fp32 pipe.
 // ------------------------------------------------------------------------------------------------
@@ -49,8 +80,9 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t& hi2, uint32_t
 // ------------------------------------------------------------------------------------------------
 struct EpiEncode {
   static constexpr int kCols = 32;
-  static constexpr int kWarpStageBytes = 0;
+  static constexpr int kWarpStageBytes = 4096;
   struct Params {
+    CUtensorMap out_hi, out_lo;    // store maps of c_hi / c_lo: [M][B][n], box 32 x 32
     const float* bias;             // [M, n] or nullptr
     const unsigned char* mask;     // [M, n] (1 = coefficient unused) or nullptr
     __nv_bfloat16* c_hi;           // [M, B, n]
@@ -64,10 +96,11 @@ struct EpiEncode {
   const Params& P;
   const TileCoord& T;
   int m_total, n_total;
+  uint8_t* stage;
   float l1 = 0.f;
   int nnz = 0;
-  __device__ EpiEncode(const Params& p, const TileCoord& t, int m, int n, uint8_t*)
-      : P(p), T(t), m_total(m), n_total(n) {}
+  __device__ EpiEncode(const Params& p, const TileCoord& t, int m, int n, uint8_t* st)
+      : P(p), T(t), m_total(m), n_total(n), stage(st) {}
 
   __device__ __forceinline__ void chunk(int c, const uint32_t (&r)[32]) {
     const int col = T.col0 + c;
@@ -127,12 +160,11 @@ struct EpiEncode {
     if (row_ok) {
       l1 += ls;
       nnz += cnt;
-      const long long off = (long long)T.model * P.c_model_stride + (long long)T.row * P.ldc + col;
-      store_bf16x32(P.c_hi + off, whi, n_total - col);
-      store_bf16x32(P.c_lo + off, wlo, n_total - col);
     }
+    stage_and_store(stage, T.lane, whi, wlo, &P.out_hi, &P.out_lo, col, T.m_blk * kBM + T.warp_q * 32, T.model);
   }
   __device__ __forceinline__ void finish() {
+    if (T.lane == 0) tma_store_wait_read();  // the staging tiles must outlive their bulk stores
     const float a = warp_sum(l1), b = warp_sum(float(nnz));
     if (T.lane == 0) {
       float* o = P.part +
@@ -205,8 +237,9 @@ struct EpiDecode {
 // ------------------------------------------------------------------------------------------------
 struct EpiDcode {
   static constexpr int kCols = 32;
-  static constexpr int kWarpStageBytes = 0;
+  static constexpr int kWarpStageBytes = 4096;
   struct Params {
+    CUtensorMap out_hi, out_lo;    // store maps of dz_hi / dz_lo: [M][B][n], box 32 x 32
     const __nv_bfloat16* c_hi;     // [M, B, n]
     const float* l1_over_b;        // [M]: alpha_m / B
     __nv_bfloat16* dz_hi;          // [M, B, n]
@@ -219,9 +252,10 @@ struct EpiDcode {
   const Params& P;
   const TileCoord& T;
   int m_total, n_total;
+  uint8_t* stage;
   float aB;
-  __device__ EpiDcode(const Params& p, const TileCoord& t, int m, int n, uint8_t*)
-      : P(p), T(t), m_total(m), n_total(n) {
+  __device__ EpiDcode(const Params& p, const TileCoord& t, int m, int n, uint8_t* st)
+      : P(p), T(t), m_total(m), n_total(n), stage(st) {
     aB = __ldg(P.l1_over_b + T.model);
   }
 
@@ -254,10 +288,7 @@ struct EpiDcode {
       dz[j + 1] = v1;
       split2(v0, v1, whi[j >> 1], wlo[j >> 1]);
     }
-    if (row_ok) {
-      store_bf16x32(P.dz_hi + off, whi, n_total - col);
-      store_bf16x32(P.dz_lo + off, wlo, n_total - col);
-    }
+    stage_and_store(stage, T.lane, whi, wlo, &P.out_hi, &P.out_lo, col, T.m_blk * kBM + T.warp_q * 32, T.model);
     if (P.db_part) {
       // transpose-reduce: 32 lanes x 32 columns -> lane j holds the sum of column j (31 shuffles)
 #pragma unroll
@@ -274,7 +305,9 @@ struct EpiDcode {
         P.db_part[(((long long)T.model * P.tiles_m + T.m_blk) * 4 + T.warp_q) * n_total + col + T.lane] = dz[0];
     }
   }
-  __device__ __forceinline__ void finish() {}
+  __device__ __forceinline__ void finish() {
+    if (T.lane == 0) tma_store_wait_read();
+  }
 };
 
 }  // namespace sce

@@ -54,8 +54,8 @@ struct GemmSmem {
   static constexpr int kBTile = BN * BK * 2;
   static constexpr int kStage = 2 * kATile + 2 * kBTile;
   static constexpr int kBarOff = STAGES * kStage;
-  static constexpr int kEpiOff = kBarOff + 256;  // barriers + tmem ptr live in the 256 bytes before
-  static constexpr int kBytes = kEpiOff + 4 * EPI_WARP_BYTES + 1024 /*align slack*/;
+  static constexpr int kEpiOff = kBarOff + 1024;  // barriers + tmem ptr live in the 1 KB before (keeps 1 KB alignment)
+  static constexpr int kBytes = kEpiOff + kEpiWarps * EPI_WARP_BYTES + 1024 /*align slack*/;
   static_assert(kBytes <= 232448, "exceeds the 227 KB of shared memory one CTA may use");
 };
 
@@ -247,7 +247,7 @@ gemm_split_kernel(const __grid_constant__ GemmParams<typename Epi::Params> p) {
       tc.warp_q = wq;
       tc.grp = grp;
       tc.lane = lane;
-      Epi epi(p.epi, tc, p.m_total, p.n_total, smem + SM::kEpiOff + wq * Epi::kWarpStageBytes);
+      Epi epi(p.epi, tc, p.m_total, p.n_total, smem + SM::kEpiOff + (grp * 4 + wq) * Epi::kWarpStageBytes);
 
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();

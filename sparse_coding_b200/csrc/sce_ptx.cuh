@@ -87,6 +87,20 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+// TMA store: shared -> global through a tiled tensor map (bulk async-group completion). Elements of the
+// box that fall outside the tensor are clipped, so ragged tile edges need no predication.
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all committed bulk stores of this thread have finished READING shared memory (it may be rewritten)
+__device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
 // ----------------------------------------------------------------------------------------------
 // tcgen05: tensor memory allocation
 // ----------------------------------------------------------------------------------------------

@@ -29,19 +29,33 @@ inline EncodeTiledFn get_encode_fn() {
 // A bf16 tensor seen as [models][rows][cols] (cols contiguous), tiled in boxes of
 // [1][box_rows][64] with the 128-byte swizzle. `models == 1` + coordinate 0 expresses an operand
 // shared by the whole ensemble. Out-of-bounds box elements read as zero.
-inline bool make_tmap_bf16(CUtensorMap* map, const void* base, uint64_t models, uint64_t rows,
-                           uint64_t cols, uint64_t row_pitch_elems, uint64_t model_pitch_elems,
-                           uint32_t box_rows) {
+inline bool make_tmap_bf16_box(CUtensorMap* map, const void* base, uint64_t models, uint64_t rows,
+                               uint64_t cols, uint64_t row_pitch_elems, uint64_t model_pitch_elems,
+                               uint32_t box_cols, uint32_t box_rows, CUtensorMapSwizzle swizzle) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return false;
   cuuint64_t dims[3] = {cols, rows, models};
   cuuint64_t strides[2] = {row_pitch_elems * 2, model_pitch_elems * 2};
-  cuuint32_t box[3] = {64, box_rows, 1};
+  cuuint32_t box[3] = {box_cols, box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims,
-                  strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
+}
+
+inline bool make_tmap_bf16(CUtensorMap* map, const void* base, uint64_t models, uint64_t rows,
+                           uint64_t cols, uint64_t row_pitch_elems, uint64_t model_pitch_elems,
+                           uint32_t box_rows) {
+  return make_tmap_bf16_box(map, base, models, rows, cols, row_pitch_elems, model_pitch_elems, 64, box_rows,
+                            CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
+// Epilogue store map: boxes of [1][32 rows][32 cols] bf16 (64-byte rows, 64-byte swizzle).
+inline bool make_tmap_bf16_store32(CUtensorMap* map, const void* base, uint64_t models, uint64_t rows,
+                                   uint64_t cols, uint64_t model_pitch_elems) {
+  return make_tmap_bf16_box(map, base, models, rows, cols, cols, model_pitch_elems, 32, 32,
+                            CU_TENSOR_MAP_SWIZZLE_64B);
 }
 
 }  // namespace sce
