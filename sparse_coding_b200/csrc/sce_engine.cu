@@ -237,12 +237,12 @@ static int build_maps(sce_plan* p, int B, BatchMaps** out) {
 // ------------------------------------------------------------------------------------------------
 // GEMM launcher
 // ------------------------------------------------------------------------------------------------
-template <class Epi, int BN, int BK, bool A_MN, bool B_MN, int STAGES>
+template <class Epi, int BN, int BK, bool A_MN, bool B_MN, int STAGES, bool SPLIT_ACC = false>
 static int launch_gemm_t(const sce_plan* p, const GemmMaps& maps, int nsets, const int* a_batched,
                          const int* b_batched, int k_total, int passes, int m_total, int n_total,
                          const typename Epi::Params& epi, cudaStream_t st) {
   using SM = GemmSmem<BN, BK, A_MN, B_MN, STAGES, Epi::kWarpStageBytes>;
-  auto kern = gemm_split_kernel<Epi, BN, BK, A_MN, B_MN, STAGES>;
+  auto kern = gemm_split_kernel<Epi, BN, BK, A_MN, B_MN, STAGES, SPLIT_ACC>;
   static bool configured = false;
   if (!configured) {
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kBytes));
@@ -413,10 +413,10 @@ static int run_pipeline(sce_plan* p, const float* x, int B, float* x_hat, bool b
   dp.gscale = 2.0f / ((float)B * (float)dd);
   if (dd > 128) {
     dp.tiles_n = (dd + 255) / 256;
-    rc = launch_gemm_t<EpiDecode, 256, 64, false, true, 2>(p, maps->decode, 1, one, one, n, d.fwd_passes, B, dd, dp, st);
+    rc = launch_gemm_t<EpiDecode, 256, 64, false, true, 2, true>(p, maps->decode, 1, one, one, n, d.fwd_passes, B, dd, dp, st);
   } else {
     dp.tiles_n = 1;
-    rc = launch_gemm_t<EpiDecode, 128, 64, false, true, 3>(p, maps->decode, 1, one, one, n, d.fwd_passes, B, dd, dp, st);
+    rc = launch_gemm_t<EpiDecode, 128, 64, false, true, 3, true>(p, maps->decode, 1, one, one, n, d.fwd_passes, B, dd, dp, st);
   }
   if (rc) return rc;
   ++launches;

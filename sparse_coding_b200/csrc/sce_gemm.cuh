@@ -62,7 +62,13 @@ struct GemmSmem {
 // ------------------------------------------------------------------------------------------------
 // The kernel
 // ------------------------------------------------------------------------------------------------
-template <class Epi, int BN, int BK, bool A_MN, bool B_MN, int STAGES>
+// SPLIT_ACC: keep the dominant hi*hi products and the small cross terms (hi*lo, lo*hi) in two separate
+// TMEM accumulators (summed in the epilogue). The tensor core's fp32 accumulation truncates, which biases a
+// result by about -2e-8 per accumulated MMA (measured: 1.3e-4 at K = 32768 with all three passes in one
+// chain); the cross terms are 2^-8 of the total, so moving them out shortens the chain that matters 3x.
+// Costs the second accumulator stage (tile epilogue no longer overlaps the next main loop), so it is used
+// where the reduction is long and the epilogue short: the decode GEMM (K = n).
+template <class Epi, int BN, int BK, bool A_MN, bool B_MN, int STAGES, bool SPLIT_ACC = false>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_split_kernel(const __grid_constant__ GemmParams<typename Epi::Params> p) {
   static_assert(BN % 64 == 0 && BN <= 256, "BN must be a multiple of 64, at most 256");
@@ -73,6 +79,7 @@ gemm_split_kernel(const __grid_constant__ GemmParams<typename Epi::Params> p) {
   constexpr int EC = Epi::kCols;  // accumulator columns handed to the epilogue per call (32 or 64)
   static_assert(EC == 32 || EC == 64, "epilogue chunk is 32 or 64 columns");
   static_assert(BN % EC == 0, "tile width must be a multiple of the epilogue chunk");
+  constexpr int kAccStages = SPLIT_ACC ? 1 : 2;
   constexpr uint32_t kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
                                  : (2 * BN <= 256) ? 256 : 512;
 
@@ -193,6 +200,7 @@ gemm_split_kernel(const __grid_constant__ GemmParams<typename Epi::Params> p) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + uint32_t(acc * BN);
+        const uint32_t d_cross = SPLIT_ACC ? tmem_base + uint32_t(BN) : d_tmem;
         uint32_t accumulate = 0;
         for (int it = 0; it < p.nsets * kblocks; ++it) {
           mbar_wait(&full_bar[stage], phase);
@@ -209,9 +217,9 @@ gemm_split_kernel(const __grid_constant__ GemmParams<typename Epi::Params> p) {
               const uint64_t al = make_sdesc_sw128(sa_lo + k * a_kstep, a_lbo, 1024);
               const uint64_t bl = make_sdesc_sw128(sb_lo + k * b_kstep, b_lbo, 1024);
               // small cross terms first, then the dominant hi*hi term
-              umma_bf16(d_tmem, al, bh, idesc, accumulate);
-              umma_bf16(d_tmem, ah, bl, idesc, 1);
-              umma_bf16(d_tmem, ah, bh, idesc, 1);
+              umma_bf16(d_cross, al, bh, idesc, accumulate);
+              umma_bf16(d_cross, ah, bl, idesc, 1);
+              umma_bf16(d_tmem, ah, bh, idesc, SPLIT_ACC ? accumulate : 1u);
             } else {
               umma_bf16(d_tmem, ah, bh, idesc, accumulate);
             }
@@ -224,7 +232,7 @@ gemm_split_kernel(const __grid_constant__ GemmParams<typename Epi::Params> p) {
           }
         }
         umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
-        if (++acc == 2) {
+        if (++acc == kAccStages) {
           acc = 0;
           acc_phase ^= 1;
         }
@@ -259,6 +267,16 @@ gemm_split_kernel(const __grid_constant__ GemmParams<typename Epi::Params> p) {
         uint32_t r[EC];
         tmem_ld32(taddr + uint32_t(c * EC), *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
         if constexpr (EC == 64) tmem_ld32(taddr + uint32_t(c * EC + 32), *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
+        if constexpr (SPLIT_ACC) {
+          static_assert(!SPLIT_ACC || EC == 32, "split accumulators are read in 32-column chunks");
+          if (three) {
+            uint32_t x[32];
+            tmem_ld32(taddr + uint32_t(BN + c * EC), x);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + __uint_as_float(x[i]));
+          }
+        }
         tmem_ld_wait();
         if (c + 2 >= kChunks) {
           // all TMEM reads of this accumulator are done: hand it back to the MMA warp early
@@ -269,7 +287,7 @@ gemm_split_kernel(const __grid_constant__ GemmParams<typename Epi::Params> p) {
         epi.chunk(c * EC, r);
       }
       epi.finish();
-      if (++acc == 2) {
+      if (++acc == kAccStages) {
         acc = 0;
         acc_phase ^= 1;
       }

@@ -239,3 +239,100 @@ def test_config2_shape_properties():
         first = loss["loss"].clone() if first is None else first
     assert bool((loss["loss"] < first).all())
     assert all(torch.isfinite(v).all() for v in ens.params.values())
+
+
+@pytest.mark.parametrize("shape", [
+    # (kind, M, d, n, B)  — the non-headline BASELINE configs at their real widths, reduced batch
+    ("topk", 3, 768, 3072, 512),      # config 3: GPT-2-small residual, TopK k in {16, 32, 64}
+    ("topk", 2, 768, 12288, 256),     # config 3: largest dictionary
+    ("tied", 1, 2048, 32768, 256),    # config 5: Pythia-1.4b MLP-out, dict_ratio 16
+    ("untied", 2, 768, 3072, 384),    # untied at GPT-2 width
+])
+def test_other_config_shapes(shape):
+    """Forward quantities (x̂, loss) on a row slice and one optimiser step at the widths of BASELINE configs 3/5."""
+    import sparse_coding_b200 as S
+    kind, M, d, n, B = shape
+    torch.manual_seed(0)
+    if kind == "topk":
+        models = [S.TopKEncoder.init(d, n, k) for k in (16, 32, 64)[:M]]
+        sig = S.TopKEncoder
+    elif kind == "tied":
+        models = [S.FunctionalTiedSAE.init(d, n, 1e-3) for _ in range(M)]
+        sig = S.FunctionalTiedSAE
+    else:
+        models = [S.FunctionalSAE.init(d, n, a) for a in (1e-3, 1e-2)[:M]]
+        sig = S.FunctionalSAE
+    ens = S.FunctionalEnsemble(models, sig, S.adam, {"lr": 1e-3}, device="cuda", no_stacking=(kind == "topk"))
+    X = torch.randn(B, d, generator=torch.Generator().manual_seed(1)).cuda()
+    loss, aux, x_hat = ens.forward_batch(X, return_x_hat=True)
+    rows = torch.arange(0, B, 7, device="cuda")
+    code = aux["c"].dense() if kind == "topk" else None
+    for m in range(M):
+        p = {k: v[m].double() for k, v in ens.params.items()}
+        if kind == "topk":
+            # Near-ties at the k-th score may legitimately resolve differently in fp32-split and fp64 arithmetic
+            # (Q8: torch.topk leaves ties unspecified), so: (i) the engine's support must be a valid top-k of the
+            # fp64 scores up to rounding, (ii) x̂ / loss are compared on that support.
+            k = int(ens.buffers["sparsity"][m])
+            Wn, _ = O.unit_rows(p["dict"], floor=None)
+            S = X.double() @ Wn.T
+            support = code[m] > 0
+            assert int(support.sum(-1).max()) <= k and int(support.sum(-1).min()) >= k - 1
+            lowest_kept = torch.where(support, S, torch.full_like(S, float("inf"))).min(-1).values
+            highest_dropped = torch.where(support, torch.full_like(S, -float("inf")), S).max(-1).values
+            assert bool((lowest_kept >= highest_dropped - 1e-4).all())
+            xh = (S.clamp(min=0) * support) @ Wn
+            f = {"x_hat": xh[rows]}
+            full = {"loss": (X.double() - xh).pow(2).mean()}
+        elif kind == "tied":
+            f = O.tied_forward(p["encoder"], p["encoder_bias"], X[rows].double(), float(ens.buffers["l1_alpha"][m]))
+            full = O.tied_forward(p["encoder"], p["encoder_bias"], X.double(), float(ens.buffers["l1_alpha"][m]))
+        else:
+            f = O.untied_forward(p["encoder"], p["encoder_bias"], p["decoder"], X[rows].double(),
+                                 float(ens.buffers["l1_alpha"][m]))
+            full = O.untied_forward(p["encoder"], p["encoder_bias"], p["decoder"], X.double(),
+                                    float(ens.buffers["l1_alpha"][m]))
+        assert relnorm(x_hat[m][rows], f["x_hat"]) <= REL, (shape, m, relnorm(x_hat[m][rows], f["x_hat"]))
+        assert abs(float(loss["loss"][m]) - float(full["loss"])) <= REL * float(full["loss"])
+    before = loss["loss"].clone()
+    for _ in range(3):
+        after, _ = ens.step_batch(X)
+    assert bool((after["loss"] < before).all()) and all(torch.isfinite(v).all() for v in ens.params.values())
+
+
+def test_fvu_and_l0_match_reference_after_training():
+    """The quality half of the metric ("FVU vs ref"): train engine and oracle from the same initial state on the
+    same 300 batches, export LearnedDicts, compare FVU (standard_metrics.py:310-314) and mean L0 (:305-308) on
+    held-out data."""
+    import sparse_coding_b200 as S
+    from sparse_coding_b200.train_loop import unstacked_to_learned_dicts
+    torch.manual_seed(0)
+    d, n, B = 64, 256, 512
+    models = [S.FunctionalTiedSAE.init(d, n, a) for a in (3e-4, 1e-3, 3e-3)]
+    clone = lambda ms: [({k: v.clone() for k, v in p.items()}, {k: v.clone() for k, v in b.items()}) for p, b in ms]
+    ens = S.FunctionalEnsemble(clone(models), S.FunctionalTiedSAE, S.adam, {"lr": 1e-3}, device="cuda")
+    ref = O.RefPortEnsemble(clone(models), O.SIG_LOSSES["tied"], lr=1e-3)
+    gen = torch.Generator().manual_seed(1)
+    feats = torch.randn(384, d, generator=gen)
+    feats /= feats.norm(dim=-1, keepdim=True)
+
+    def batch(rows):
+        codes = (torch.rand(rows, 384, generator=gen) < 0.03).float() * torch.rand(rows, 384, generator=gen)
+        return codes @ feats + 0.01 * torch.randn(rows, d, generator=gen)
+
+    for _ in range(300):
+        X = batch(B)
+        ens.step_batch(X.cuda())
+        ref.step_batch(X)
+    held = batch(4096)
+    mine = unstacked_to_learned_dicts(ens, {"dict_size": n}, ["dict_size"], ["l1_alpha"])
+    for i, (ld, hp) in enumerate(mine):
+        rp = {k: v[i] for k, v in ref.params.items()}
+        rb = {k: v[i] for k, v in ref.buffers.items()}
+        rld = S.FunctionalTiedSAE.to_learned_dict(rp, rb)
+        fvu_e, fvu_r = float(O.fvu(held, ld.predict(held))), float(O.fvu(held, rld.predict(held)))
+        l0_e = float((ld.encode(ld.center(held)) != 0).float().sum(-1).mean())
+        l0_r = float((rld.encode(rld.center(held)) != 0).float().sum(-1).mean())
+        assert abs(fvu_e - fvu_r) <= 0.01 * fvu_r + 1e-4, (i, fvu_e, fvu_r)
+        assert abs(l0_e - l0_r) <= 0.01 * l0_r + 0.05, (i, l0_e, l0_r)
+        assert fvu_r < 0.5                                      # it actually learned something
