@@ -351,11 +351,7 @@ static int run_pipeline(sce_plan* p, const float* x, int B, float* x_hat, bool b
     ep.out_lo = maps->st_c_lo;
     ep.bias = p->b.encoder_bias;
     ep.mask = p->b.coef_mask;
-    ep.c_hi = p->c_hi;
-    ep.c_lo = p->c_lo;
     ep.part = p->part_enc;
-    ep.c_model_stride = Bm * n;
-    ep.ldc = n;
     ep.tiles_m = tiles_mB;
     ep.flag_zero = 1;
     if (n > 128) {
@@ -440,8 +436,6 @@ static int run_pipeline(sce_plan* p, const float* x, int B, float* x_hat, bool b
     zp.out_lo = maps->st_dz_lo;
     zp.c_hi = p->c_hi;
     zp.l1_over_b = p->l1_over_b;
-    zp.dz_hi = p->dz_hi;
-    zp.dz_lo = p->dz_lo;
     zp.db_part = p->b.encoder_bias ? p->db_part : nullptr;
     zp.c_model_stride = Bm * n;
     zp.ldc = n;
@@ -461,8 +455,8 @@ static int run_pipeline(sce_plan* p, const float* x, int B, float* x_hat, bool b
       sp.model_stride = (long long)n * dd;
       sp.ld = dd;
       if (dd > 128)
-        return launch_gemm_t<EpiStoreF32, 256, kBkDw, true, true, 4>(p, gm, nsets, ab, bb, B, d.bwd_passes, n, dd, sp, st);
-      return launch_gemm_t<EpiStoreF32, 128, kBkDw, true, true, 6>(p, gm, nsets, ab, bb, B, d.bwd_passes, n, dd, sp, st);
+        return launch_gemm_t<EpiStoreF32, 256, kBkDw, true, true, 4, true>(p, gm, nsets, ab, bb, B, d.bwd_passes, n, dd, sp, st);
+      return launch_gemm_t<EpiStoreF32, 128, kBkDw, true, true, 6, true>(p, gm, nsets, ab, bb, B, d.bwd_passes, n, dd, sp, st);
     };
     if (d.variant == SCE_UNTIED) {
       rc = dw(maps->dw_enc, 1, one, xb, p->dw_enc);

@@ -85,11 +85,7 @@ struct EpiEncode {
     CUtensorMap out_hi, out_lo;    // store maps of c_hi / c_lo: [M][B][n], box 32 x 32
     const float* bias;             // [M, n] or nullptr
     const unsigned char* mask;     // [M, n] (1 = coefficient unused) or nullptr
-    __nv_bfloat16* c_hi;           // [M, B, n]
-    __nv_bfloat16* c_lo;
     float* part;                   // [M][tiles_m*8][tiles_n][2]  (sum c, nnz)
-    long long c_model_stride;      // batch_max*n
-    int ldc;                       // n
     int tiles_m, tiles_n;
     int flag_zero;                 // 1: mark z == 0 with -0.0 (clamp semantics), 0: relu semantics
   };
@@ -242,8 +238,6 @@ struct EpiDcode {
     CUtensorMap out_hi, out_lo;    // store maps of dz_hi / dz_lo: [M][B][n], box 32 x 32
     const __nv_bfloat16* c_hi;     // [M, B, n]
     const float* l1_over_b;        // [M]: alpha_m / B
-    __nv_bfloat16* dz_hi;          // [M, B, n]
-    __nv_bfloat16* dz_lo;
     float* db_part;                // [M][tiles_m*4][n] or nullptr (no bias)
     long long c_model_stride;      // batch_max*n
     int ldc;                       // n

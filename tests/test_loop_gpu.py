@@ -174,3 +174,25 @@ def test_host_fed_step_through_c_abi():
     assert torch.equal(losses[:, 0], la["loss"].cpu())
     assert torch.equal(ens_a.params["encoder"], ens_b.params["encoder"])
     assert lib.sce_get_step_count(ens_b._plan) == 1
+
+
+def test_on_device_evaluation_matches_learned_dict_metrics():
+    """metrics.evaluate (one fused forward for all models) == FVU / mean L0 / ever-active computed the reference's
+    way from the exported LearnedDicts (standard_metrics.py:305-314, 446-454)."""
+    import sparse_coding_b200 as S
+    from sparse_coding_b200.metrics import evaluate
+    torch.manual_seed(0)
+    d, n = 64, 256
+    models = [S.FunctionalTiedSAE.init(d, n, a) for a in (1e-3, 1e-2)]
+    ens = S.FunctionalEnsemble(models, S.FunctionalTiedSAE, S.adam, {"lr": 1e-3}, device="cuda")
+    gen = torch.Generator().manual_seed(3)
+    for _ in range(20):
+        ens.step_batch(torch.randn(256, d, generator=gen).cuda())
+    held = torch.randn(1000, d, generator=gen)
+    got = evaluate(ens, held.cuda(), n_ever_active=True)
+    for i, (p, b) in enumerate(ens.unstack(device="cpu")):
+        ld = S.FunctionalTiedSAE.to_learned_dict(p, b)
+        c = ld.encode(ld.center(held))
+        assert abs(float(got["fvu"][i]) - float(O.fvu(held, ld.predict(held)))) <= 1e-4 * float(got["fvu"][i]) + 1e-6
+        assert abs(float(got["mean_l0"][i]) - float((c != 0).float().sum(-1).mean())) <= 0.02
+        assert abs(int(got["n_ever_active"][i]) - int((c != 0).any(0).sum())) <= 1
