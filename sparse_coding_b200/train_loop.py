@@ -70,11 +70,19 @@ def _batch_index_lists(sampler) -> Iterable[torch.Tensor]:
     bs = getattr(sampler, "batch_size", None)
     if isinstance(sampler, torch.utils.data.BatchSampler) and isinstance(inner, torch.utils.data.RandomSampler) \
             and not inner.replacement and inner.num_samples == len(inner.data_source):
-        perm = torch.tensor(list(iter(inner)), dtype=torch.int64)
-        n_full = len(perm) // bs * bs
+        # what RandomSampler.__iter__ does, minus the 2M-element Python list: seed a private generator from the
+        # global RNG (or use the sampler's own), draw one permutation
+        n = len(inner.data_source)
+        if inner.generator is None:
+            gen = torch.Generator()
+            gen.manual_seed(int(torch.empty((), dtype=torch.int64).random_().item()))
+        else:
+            gen = inner.generator
+        perm = torch.randperm(n, generator=gen)
+        n_full = n // bs * bs
         for i in range(0, n_full, bs):
             yield perm[i:i + bs]
-        if n_full < len(perm) and not sampler.drop_last:
+        if n_full < n and not sampler.drop_last:
             yield perm[n_full:]
         return
     for idxs in sampler:
