@@ -185,6 +185,7 @@ class FunctionalEnsemble:
         self._plan = None
         self._plan_key = None
         self._ws = None
+        self._centering = None
         self._serial = 0
         self._steps = 0
         main = "dict" if variant == "topk" else "encoder"
@@ -203,8 +204,15 @@ class FunctionalEnsemble:
         return dev
 
     def _needs_centering(self) -> bool:
+        """Whether the tied signature's centring is non-trivial. Evaluated once (it costs three device
+        reductions and a host sync) and cached until ``refresh()`` / ``to_device()``."""
         if self._variant != "tied":
             return False
+        if self._centering is None:
+            self._centering = self._centering_is_nontrivial()
+        return self._centering
+
+    def _centering_is_nontrivial(self) -> bool:
         b = self.buffers
         d = self._d
         eye = torch.eye(d, device=b["center_rot"].device, dtype=b["center_rot"].dtype)
@@ -372,7 +380,9 @@ class FunctionalEnsemble:
             return g, (self._losses_dict(), self._aux(B))
 
     def refresh(self):
-        """Call after modifying ``params`` from outside the engine (re-derives the bf16 operand copies)."""
+        """Call after modifying ``params`` / ``buffers`` from outside the engine (re-derives the bf16 operand
+        copies and the cached centring check)."""
+        self._centering = None
         if self._plan is not None:
             with torch.cuda.device(torch.device(self.device)):
                 _lib.check(_lib.load().sce_prepare(self._plan, self._stream()), "sce_prepare")
@@ -428,6 +438,7 @@ class FunctionalEnsemble:
     def to_device(self, device):
         self._destroy_plan()
         self._plan_key = None
+        self._centering = None
         self.device = device
         self.params = _tree_map(lambda t: t.to(device), self.params)
         self.buffers = _tree_map(lambda t: t.to(device), self.buffers)
