@@ -67,6 +67,7 @@ struct sce_plan {
   float *part_enc, *part_dec, *db_part, *bnorm, *l1_over_b, *loss_stage, *nnz_stage;
   int tiles_mB_max;
   std::map<int, BatchMaps*>* maps;
+  int bk_encode, bk_decode, bk_dcode;  // K block (64: 128-byte swizzle, 32: 64-byte swizzle) of the K-major GEMMs
   int last_launches;
   long long step;  // number of optimiser steps taken
   // optional per-phase device timing (sce_profile_*): events bracket each phase of a step
@@ -174,9 +175,29 @@ static size_t carve(sce_plan* p, const sce_desc& d, uint8_t* base) {
 // ------------------------------------------------------------------------------------------------
 static int bn_for(int N) { return N > 128 ? 256 : 128; }
 constexpr int kBkDw = 32;  // K block of the MN-major weight-gradient GEMM
+// K block of the GEMMs with K-major operands: 32 (64-byte swizzle, 4 stages of 48 KB at BN = 256) keeps three
+// stages in flight behind the one being multiplied; 64 (128-byte swizzle) only has room for two stages.
+// Chosen per GEMM (plan fields bk_encode / bk_decode / bk_dcode; env SCE_TUNE_BK_{ENCODE,DECODE,DCODE} overrides):
+// measured on B200 (profiles/r01f_bk_tuning.txt) the deeper pipeline wins where the A operand streams from HBM
+// (decode: the code tensor) and loses where both operands are L2-resident (encode, dcode: twice the TMA requests).
+static int tune_bk(const char* env, int dflt) {
+  const char* v = getenv(env);
+  if (!v) return dflt;
+  const int k = atoi(v);
+  return (k == 32 || k == 64) ? k : dflt;
+}
+static CUtensorMapSwizzle swizzle_for_bk(int bk) {
+  return bk == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
+}
 
+// dictionary operand [M][n][d]; `kmajor`: box = [box_rows][kBkK] with the K-major swizzle, else [box_rows][64]
 static bool map2(CUtensorMap* hi, CUtensorMap* lo, const void* phi, const void* plo, uint64_t models,
-                 uint64_t rows, uint64_t cols, uint32_t box_rows) {
+                 uint64_t rows, uint64_t cols, uint32_t box_rows, int kmajor_bk) {
+  if (kmajor_bk)
+    return make_tmap_bf16_box(hi, phi, models, rows, cols, cols, rows * cols, kmajor_bk, box_rows,
+                              swizzle_for_bk(kmajor_bk)) &&
+           make_tmap_bf16_box(lo, plo, models, rows, cols, cols, rows * cols, kmajor_bk, box_rows,
+                              swizzle_for_bk(kmajor_bk));
   return make_tmap_bf16(hi, phi, models, rows, cols, cols, rows * cols, box_rows) &&
          make_tmap_bf16(lo, plo, models, rows, cols, cols, rows * cols, box_rows);
 }
@@ -195,20 +216,25 @@ static int build_maps(sce_plan* p, int B, BatchMaps** out) {
   // NOTE: activations are laid out with the plan's batch_max pitch between models; only `B` rows are
   // visible through the map, so rows >= B read as zero (TMA out-of-bounds fill).
   auto act = [&](CUtensorMap* hi, CUtensorMap* lo, const void* phi, const void* plo, uint64_t models,
-                 uint64_t cols, uint32_t box_rows) {
+                 uint64_t cols, uint32_t box_rows) {   // MN-major use: box = [box_rows k][64]
     return make_tmap_bf16(hi, phi, models, (uint64_t)B, cols, cols, Bm * cols, box_rows) &&
            make_tmap_bf16(lo, plo, models, (uint64_t)B, cols, cols, Bm * cols, box_rows);
   };
+  auto actk = [&](CUtensorMap* hi, CUtensorMap* lo, const void* phi, const void* plo, uint64_t models,
+                  uint64_t cols, int bk) {              // K-major A operand: box = [128 rows][bk]
+    return make_tmap_bf16_box(hi, phi, models, (uint64_t)B, cols, cols, Bm * cols, bk, kBM, swizzle_for_bk(bk)) &&
+           make_tmap_bf16_box(lo, plo, models, (uint64_t)B, cols, cols, Bm * cols, bk, kBM, swizzle_for_bk(bk));
+  };
   bool ok = true;
   // encode: A = x [xm,B,d] K-major, B = Wenc [M,n,d] K-major
-  ok &= act(&m->encode.a_hi[0], &m->encode.a_lo[0], p->x_hi, p->x_lo, xm, dd, kBM);
-  ok &= map2(&m->encode.b_hi[0], &m->encode.b_lo[0], p->wenc_hi, p->wenc_lo, M, n, dd, bn_for(d.n));
+  ok &= actk(&m->encode.a_hi[0], &m->encode.a_lo[0], p->x_hi, p->x_lo, xm, dd, p->bk_encode);
+  ok &= map2(&m->encode.b_hi[0], &m->encode.b_lo[0], p->wenc_hi, p->wenc_lo, M, n, dd, bn_for(d.n), p->bk_encode);
   // decode: A = c [M,B,n] K-major, B = Wdec [M,n,d] MN-major (box = 64 k-rows x 64 columns)
-  ok &= act(&m->decode.a_hi[0], &m->decode.a_lo[0], p->c_hi, p->c_lo, M, n, kBM);
-  ok &= map2(&m->decode.b_hi[0], &m->decode.b_lo[0], p->wdec_hi, p->wdec_lo, M, n, dd, 64);
+  ok &= actk(&m->decode.a_hi[0], &m->decode.a_lo[0], p->c_hi, p->c_lo, M, n, p->bk_decode);
+  ok &= map2(&m->decode.b_hi[0], &m->decode.b_lo[0], p->wdec_hi, p->wdec_lo, M, n, dd, p->bk_decode, 0);
   // dcode: A = g [M,B,d] K-major, B = Wdec K-major
-  ok &= act(&m->dcode.a_hi[0], &m->dcode.a_lo[0], p->g_hi, p->g_lo, M, dd, kBM);
-  ok &= map2(&m->dcode.b_hi[0], &m->dcode.b_lo[0], p->wdec_hi, p->wdec_lo, M, n, dd, bn_for(d.n));
+  ok &= actk(&m->dcode.a_hi[0], &m->dcode.a_lo[0], p->g_hi, p->g_lo, M, dd, p->bk_dcode);
+  ok &= map2(&m->dcode.b_hi[0], &m->dcode.b_lo[0], p->wdec_hi, p->wdec_lo, M, n, dd, bn_for(d.n), p->bk_dcode);
   // weight gradients: everything MN-major, reduction over the batch rows
   if (d.variant == SCE_UNTIED) {
     ok &= act(&m->dw_enc.a_hi[0], &m->dw_enc.a_lo[0], p->dz_hi, p->dz_lo, M, n, kBkDw);
@@ -274,8 +300,12 @@ static int launch_gemm_t(const sce_plan* p, const GemmMaps& maps, int nsets, con
   return SCE_OK;
 }
 
-// BN is chosen from the output width; K-major GEMMs use BK = 64, the MN-major one BK = kBkDw.
-#define SCE_DISPATCH_BN(N, CALL256, CALL128) ((N) > 128 ? (CALL256) : (CALL128))
+// Dispatch a K-major-A GEMM on (output width -> BN, plan BK): BN 256/128 x BK 64/32 with 2/4 resp. 3/6 stages.
+#define SCE_LAUNCH_K(EPI, B_MN, SPLIT, WIDE, BK, ...)                                                         \
+  ((WIDE) ? ((BK) == 32 ? launch_gemm_t<EPI, 256, 32, false, B_MN, 4, SPLIT>(__VA_ARGS__)                      \
+                        : launch_gemm_t<EPI, 256, 64, false, B_MN, 2, SPLIT>(__VA_ARGS__))                     \
+          : ((BK) == 32 ? launch_gemm_t<EPI, 128, 32, false, B_MN, 6, SPLIT>(__VA_ARGS__)                      \
+                        : launch_gemm_t<EPI, 128, 64, false, B_MN, 3, SPLIT>(__VA_ARGS__)))
 
 // ------------------------------------------------------------------------------------------------
 // helpers shared by step / forward / grads
@@ -354,13 +384,9 @@ static int run_pipeline(sce_plan* p, const float* x, int B, float* x_hat, bool b
     ep.part = p->part_enc;
     ep.tiles_m = tiles_mB;
     ep.flag_zero = 1;
-    if (n > 128) {
-      ep.tiles_n = (n + 255) / 256;
-      rc = launch_gemm_t<EpiEncode, 256, 64, false, false, 2>(p, maps->encode, 1, xb, one, dd, d.fwd_passes, B, n, ep, st);
-    } else {
-      ep.tiles_n = 1;
-      rc = launch_gemm_t<EpiEncode, 128, 64, false, false, 3>(p, maps->encode, 1, xb, one, dd, d.fwd_passes, B, n, ep, st);
-    }
+    ep.tiles_n = n > 128 ? (n + 255) / 256 : 1;
+    rc = SCE_LAUNCH_K(EpiEncode, false, false, n > 128, p->bk_encode, p, maps->encode, 1, xb, one, dd, d.fwd_passes, B, n,
+                      ep, st);
     if (rc) return rc;
     ++launches;
     n_enc_parts = tiles_mB * 8 * ep.tiles_n;
@@ -370,10 +396,8 @@ static int run_pipeline(sce_plan* p, const float* x, int B, float* x_hat, bool b
     sp.out = reinterpret_cast<float*>(p->dz_hi);
     sp.model_stride = Bm * n;
     sp.ld = n;
-    if (n > 128)
-      rc = launch_gemm_t<EpiStoreF32, 256, 64, false, false, 2>(p, maps->encode, 1, xb, one, dd, d.fwd_passes, B, n, sp, st);
-    else
-      rc = launch_gemm_t<EpiStoreF32, 128, 64, false, false, 3>(p, maps->encode, 1, xb, one, dd, d.fwd_passes, B, n, sp, st);
+    rc = SCE_LAUNCH_K(EpiStoreF32, false, false, n > 128, p->bk_encode, p, maps->encode, 1, xb, one, dd, d.fwd_passes, B,
+                      n, sp, st);
     if (rc) return rc;
     ++launches;
     if ((size_t)n * 4 > 200 * 1024) return fail(SCE_ERR_INVALID, "top-k: n = %d exceeds the shared-memory row buffer", n);
@@ -407,13 +431,9 @@ static int run_pipeline(sce_plan* p, const float* x, int B, float* x_hat, bool b
   dp.ld = dd;
   dp.tiles_m = tiles_mB;
   dp.gscale = 2.0f / ((float)B * (float)dd);
-  if (dd > 128) {
-    dp.tiles_n = (dd + 255) / 256;
-    rc = launch_gemm_t<EpiDecode, 256, 64, false, true, 2, true>(p, maps->decode, 1, one, one, n, d.fwd_passes, B, dd, dp, st);
-  } else {
-    dp.tiles_n = 1;
-    rc = launch_gemm_t<EpiDecode, 128, 64, false, true, 3, true>(p, maps->decode, 1, one, one, n, d.fwd_passes, B, dd, dp, st);
-  }
+  dp.tiles_n = dd > 128 ? (dd + 255) / 256 : 1;
+  rc = SCE_LAUNCH_K(EpiDecode, true, true, dd > 128, p->bk_decode, p, maps->decode, 1, one, one, n, d.fwd_passes, B, dd, dp,
+                    st);
   if (rc) return rc;
   ++launches;
 
@@ -440,10 +460,8 @@ static int run_pipeline(sce_plan* p, const float* x, int B, float* x_hat, bool b
     zp.c_model_stride = Bm * n;
     zp.ldc = n;
     zp.tiles_m = tiles_mB;
-    if (n > 128)
-      rc = launch_gemm_t<EpiDcode, 256, 64, false, false, 2>(p, maps->dcode, 1, one, one, dd, d.bwd_passes, B, n, zp, st);
-    else
-      rc = launch_gemm_t<EpiDcode, 128, 64, false, false, 3>(p, maps->dcode, 1, one, one, dd, d.bwd_passes, B, n, zp, st);
+    rc = SCE_LAUNCH_K(EpiDcode, false, false, n > 128, p->bk_dcode, p, maps->dcode, 1, one, one, dd, d.bwd_passes, B, n, zp,
+                      st);
     if (rc) return rc;
     ++launches;
 
@@ -520,6 +538,9 @@ int sce_plan_create(const sce_desc* desc, const sce_buffers* buffers, sce_plan**
   p->b = b;
   p->sms = sms;
   p->xm = desc->x_per_model ? desc->n_models : 1;
+  p->bk_encode = tune_bk("SCE_TUNE_BK_ENCODE", 64);
+  p->bk_decode = tune_bk("SCE_TUNE_BK_DECODE", 32);
+  p->bk_dcode = tune_bk("SCE_TUNE_BK_DCODE", 64);
   p->maps = new std::map<int, BatchMaps*>();
   carve(p, *desc, static_cast<uint8_t*>(b.workspace));
   *out_plan = p;

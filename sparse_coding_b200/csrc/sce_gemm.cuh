@@ -73,8 +73,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_split_kernel(const __grid_constant__ GemmParams<typename Epi::Params> p) {
   static_assert(BN % 64 == 0 && BN <= 256, "BN must be a multiple of 64, at most 256");
   static_assert(BK % 16 == 0 && BK <= 64, "BK in {16,32,48,64}");
-  static_assert(A_MN || BK == 64, "K-major A uses one 128-byte swizzled row per tile row: BK == 64");
-  static_assert(B_MN || BK == 64, "K-major B uses one 128-byte swizzled row per tile row: BK == 64");
+  static_assert(A_MN || BK == 64 || BK == 32, "K-major A: one swizzled row per tile row, 128 B (BK=64) or 64 B (BK=32)");
+  static_assert(B_MN || BK == 64 || BK == 32, "K-major B: one swizzled row per tile row, 128 B (BK=64) or 64 B (BK=32)");
   using SM = GemmSmem<BN, BK, A_MN, B_MN, STAGES, Epi::kWarpStageBytes>;
   constexpr int EC = Epi::kCols;  // accumulator columns handed to the epilogue per call (32 or 64)
   static_assert(EC == 32 || EC == 64, "epilogue chunk is 32 or 64 columns");
@@ -192,6 +192,9 @@ gemm_split_kernel(const __grid_constant__ GemmParams<typename Epi::Params> p) {
       constexpr uint32_t b_lbo = B_MN ? BK * 128 : 16;
       constexpr uint32_t a_kstep = A_MN ? 2048 : 32;  // bytes per K=16 slice
       constexpr uint32_t b_kstep = B_MN ? 2048 : 32;
+      // MN-major tiles always use 128-byte rows; K-major tiles have BK*2-byte rows (128B or 64B swizzle)
+      constexpr uint32_t a_sbo = (A_MN || BK == 64) ? 1024 : 512, a_lt = (A_MN || BK == 64) ? 2 : 4;
+      constexpr uint32_t b_sbo = (B_MN || BK == 64) ? 1024 : 512, b_lt = (B_MN || BK == 64) ? 2 : 4;
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -211,11 +214,11 @@ gemm_split_kernel(const __grid_constant__ GemmParams<typename Epi::Params> p) {
           const uint32_t sb_lo = sb_hi + SM::kBTile;
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t ah = make_sdesc_sw128(sa_hi + k * a_kstep, a_lbo, 1024);
-            const uint64_t bh = make_sdesc_sw128(sb_hi + k * b_kstep, b_lbo, 1024);
+            const uint64_t ah = make_sdesc(sa_hi + k * a_kstep, a_lbo, a_sbo, a_lt);
+            const uint64_t bh = make_sdesc(sb_hi + k * b_kstep, b_lbo, b_sbo, b_lt);
             if (three) {
-              const uint64_t al = make_sdesc_sw128(sa_lo + k * a_kstep, a_lbo, 1024);
-              const uint64_t bl = make_sdesc_sw128(sb_lo + k * b_kstep, b_lbo, 1024);
+              const uint64_t al = make_sdesc(sa_lo + k * a_kstep, a_lbo, a_sbo, a_lt);
+              const uint64_t bl = make_sdesc(sb_lo + k * b_kstep, b_lbo, b_sbo, b_lt);
               // small cross terms first, then the dominant hi*hi term
               umma_bf16(d_cross, al, bh, idesc, accumulate);
               umma_bf16(d_cross, ah, bl, idesc, 1);

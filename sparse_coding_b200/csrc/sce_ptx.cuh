@@ -166,15 +166,23 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, bool a_mn, 
 //  * MN-major operand (non-reduction index contiguous): one "row" of 128 B holds 64 consecutive
 //    M (or N) elements of ONE k; 8 consecutive k make a 1024-B group; the next 8 k are SBO bytes
 //    further; the next 64 M/N elements are LBO bytes further.
-__device__ __forceinline__ uint64_t make_sdesc_sw128(uint32_t smem_addr, uint32_t lbo_bytes,
-                                                     uint32_t sbo_bytes) {
+//
+// K-major operands may also use the 64-byte swizzle (layout type 4): rows are 64 B (32 bf16) apart, 8-row
+// groups SBO = 512 B apart; this halves the K extent of a pipeline stage (BK = 32) so that twice as many
+// stages fit in shared memory.
+__device__ __forceinline__ uint64_t make_sdesc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                               uint32_t layout_type) {
   uint64_t d = 0;
   d |= uint64_t((smem_addr & 0x3FFFFu) >> 4);
   d |= uint64_t((lbo_bytes >> 4) & 0x3FFFu) << 16;
   d |= uint64_t((sbo_bytes >> 4) & 0x3FFFu) << 32;
   d |= uint64_t(1) << 46;
-  d |= uint64_t(2) << 61;
+  d |= uint64_t(layout_type) << 61;
   return d;
+}
+__device__ __forceinline__ uint64_t make_sdesc_sw128(uint32_t smem_addr, uint32_t lbo_bytes,
+                                                     uint32_t sbo_bytes) {
+  return make_sdesc(smem_addr, lbo_bytes, sbo_bytes, 2);
 }
 
 // ----------------------------------------------------------------------------------------------

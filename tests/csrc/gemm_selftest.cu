@@ -81,10 +81,11 @@ static void make_operand(Operand& o, int models, int rows, int K, bool mn) {
 static bool tmaps(const Operand& o, uint32_t box_rows_kmajor, int BK, CUtensorMap* hi,
                   CUtensorMap* lo) {
   if (!o.mn) {
-    return make_tmap_bf16(hi, o.s.d_hi, o.models, o.rows, o.K, o.K, (uint64_t)o.rows * o.K,
-                          box_rows_kmajor) &&
-           make_tmap_bf16(lo, o.s.d_lo, o.models, o.rows, o.K, o.K, (uint64_t)o.rows * o.K,
-                          box_rows_kmajor);
+    const CUtensorMapSwizzle sw = BK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+    return make_tmap_bf16_box(hi, o.s.d_hi, o.models, o.rows, o.K, o.K, (uint64_t)o.rows * o.K, BK,
+                              box_rows_kmajor, sw) &&
+           make_tmap_bf16_box(lo, o.s.d_lo, o.models, o.rows, o.K, o.K, (uint64_t)o.rows * o.K, BK,
+                              box_rows_kmajor, sw);
   }
   return make_tmap_bf16(hi, o.s.d_hi, o.models, o.K, o.rows, o.rows, (uint64_t)o.rows * o.K, BK) &&
          make_tmap_bf16(lo, o.s.d_lo, o.models, o.K, o.rows, o.rows, (uint64_t)o.rows * o.K, BK);
@@ -237,6 +238,14 @@ int main(int argc, char** argv) {
   ok &= run_case<256, 64, false, false, 2>("kk_multi", 3, 384, 512, 512, 1, 3, true, false);
   ok &= run_case<256, 64, false, false, 2>("kk_ragged", 2, 200, 328, 104, 1, 3, true, false);
   ok &= run_case<128, 64, false, false, 3>("kk_bn128", 2, 256, 384, 256, 1, 3, true, false);
+  // ---- K-major operands with the 64-byte swizzle (BK = 32, four stages)
+  ok &= run_case<256, 32, false, false, 4>("kk32_k16", 1, 128, 256, 16, 1, 1, false, false);
+  ok &= run_case<256, 32, false, false, 4>("kk32_k64", 1, 128, 256, 64, 1, 1, false, false);
+  ok &= run_case<256, 32, false, false, 4>("kk32_multi", 3, 384, 512, 512, 1, 3, true, false);
+  ok &= run_case<256, 32, false, false, 4>("kk32_ragged", 2, 200, 328, 104, 1, 3, true, false);
+  ok &= run_case<128, 32, false, false, 6>("kk32_bn128", 2, 256, 384, 256, 1, 3, true, false);
+  ok &= run_case<256, 32, false, true, 4>("kmn32_3pass", 2, 256, 512, 512, 1, 3, false, false);
+  ok &= run_case<256, 32, false, true, 4>("kmn32_ragged", 2, 200, 328, 104, 1, 3, false, false);
   // ---- K-major A x MN-major B (decode shape: X^ = C W)
   ok &= run_case<256, 64, false, true, 2>("kmn_k16", 1, 128, 256, 16, 1, 1, false, false);
   ok &= run_case<256, 64, false, true, 2>("kmn_k64", 1, 128, 256, 64, 1, 1, false, false);
@@ -255,6 +264,8 @@ int main(int argc, char** argv) {
     ok &= run_case<256, 32, true, true, 4>("big_dw", 4, 4096, 512, 8192, 2, 3, false, true);
     ok &= run_case<256, 64, true, true, 2>("big_dw64", 4, 4096, 512, 8192, 2, 3, false, true);
     ok &= run_case<256, 64, false, false, 2>("big_enc1p", 4, 8192, 4096, 512, 1, 1, true, false);
+    ok &= run_case<256, 32, false, false, 4>("big_encode32", 4, 8192, 4096, 512, 1, 3, true, false);
+    ok &= run_case<256, 32, false, true, 4>("big_decode32", 4, 8192, 512, 4096, 1, 3, false, false);
   }
   printf(ok ? "ALL PASS\n" : "SOME FAILED\n");
   return ok ? 0 : 1;
