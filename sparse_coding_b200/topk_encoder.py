@@ -1,8 +1,16 @@
-"""TopK dictionary: signature (training side) and learned-dict (inference side).
+"""Top-k dictionaries: the training-side signature and the exported inference object.
 
-Mirrors ``autoencoders/topk_encoder.py``: ``TopKEncoder.init`` (:10-17, **randn** dictionary on the CPU, long
-``sparsity`` buffer), ``encode`` (:19-27, top-k by SIGNED score, then ReLU), ``to_learned_dict`` (:43-46) and
-``TopKLearnedDict`` (:49-62). ``loss`` is executed by the CUDA engine (sparse_coding_b200.ensemble)."""
+Behavioural contract (reference ``autoencoders/topk_encoder.py``): the dictionary is initialised from a standard
+normal on the CPU and carries a per-model integer ``sparsity`` buffer (:10-17); a code keeps, per input row, the
+``k`` largest *signed* scores against the row-normalised dictionary and then applies a ReLU, so a row can end up
+with fewer than ``k`` non-zeros (:19-27); the loss is the plain MSE of the reconstruction, without bias or L1 term
+(:29-40); export wraps the normalised dictionary together with ``k`` (:43-62).
+
+Training-time ``loss`` runs in the CUDA engine: scores on the tensor cores, a per-row radix select
+(``topk_select_kernel``), then the same decode / backward / Adam pipeline as the tied SAE. Unlike the reference,
+which has to fall back to a Python loop over models because ``torch.topk`` with a data-dependent ``k`` cannot be
+vmapped (``no_stacking=True``), models with different ``k`` are batched in one launch sequence.
+"""
 from __future__ import annotations
 
 import torch
@@ -13,11 +21,36 @@ from .signatures import DictSignature, engine_loss
 _REF_MODULE = "autoencoders.topk_encoder"
 
 
-def topk_relu_code(scores: torch.Tensor, k: int) -> torch.Tensor:
-    idx = torch.topk(scores, k, dim=-1).indices
-    code = torch.zeros_like(scores)
-    code.scatter_(-1, idx, scores.gather(-1, idx))
-    return code.clamp(min=0.0)
+def _unit_norm_rows(mat: torch.Tensor) -> torch.Tensor:
+    # no clamp on the norm here, unlike the SAE variants
+    return mat / mat.norm(dim=-1)[:, None]
+
+
+def sparse_code_from_scores(scores: torch.Tensor, k: int) -> torch.Tensor:
+    """Keep each row's k largest entries (by signed value), zero the rest, clip negatives."""
+    k = int(k)
+    top = torch.topk(scores, k, dim=-1)
+    kept = torch.zeros_like(scores).scatter_(-1, top.indices, top.values)
+    return kept.clamp_(min=0.0)
+
+
+class TopKLearnedDict(LearnedDict):
+    """Inference object stored in ``learned_dicts.pt`` for top-k runs: attributes ``dict`` (already normalised),
+    ``sparsity``, ``n_feats``, ``activation_size``."""
+
+    def __init__(self, dict, sparsity):
+        self.dict = dict
+        self.sparsity = sparsity
+        self.n_feats, self.activation_size = dict.shape
+
+    def get_learned_dict(self):
+        return self.dict
+
+    def encode(self, x):
+        return sparse_code_from_scores(x @ self.dict.T, self.sparsity)
+
+    def to_device(self, device):
+        self.dict = self.dict.to(device)
 
 
 class TopKEncoder(DictSignature):
@@ -25,13 +58,14 @@ class TopKEncoder(DictSignature):
 
     @staticmethod
     def init(d_activation, n_features, sparsity, dtype=torch.float32):
-        params = {"dict": torch.randn(n_features, d_activation, dtype=dtype)}
-        buffers = {"sparsity": torch.tensor(sparsity, dtype=torch.long)}
-        return params, buffers
+        if not 0 < int(sparsity) <= n_features:
+            raise ValueError(f"sparsity must be in [1, {n_features}], got {sparsity}")
+        dictionary = torch.randn(n_features, d_activation, dtype=dtype)
+        return {"dict": dictionary}, {"sparsity": torch.tensor(sparsity, dtype=torch.long)}
 
     @staticmethod
     def encode(b, sparsity, normed_dict):
-        return topk_relu_code(b @ normed_dict.T, int(sparsity))
+        return sparse_code_from_scores(b @ normed_dict.T, sparsity)
 
     @staticmethod
     def loss(params, buffers, batch):
@@ -39,24 +73,7 @@ class TopKEncoder(DictSignature):
 
     @staticmethod
     def to_learned_dict(params, buffers):
-        d = params["dict"]
-        return TopKLearnedDict(d / d.norm(dim=-1)[:, None], buffers["sparsity"].item())
-
-
-class TopKLearnedDict(LearnedDict):
-    def __init__(self, dict, sparsity):
-        self.dict = dict
-        self.sparsity = sparsity
-        self.n_feats, self.activation_size = self.dict.shape
-
-    def to_device(self, device):
-        self.dict = self.dict.to(device)
-
-    def encode(self, x):
-        return TopKEncoder.encode(x, self.sparsity, self.dict)
-
-    def get_learned_dict(self):
-        return self.dict
+        return TopKLearnedDict(_unit_norm_rows(params["dict"]), buffers["sparsity"].item())
 
 
 for _cls in (TopKEncoder, TopKLearnedDict):
