@@ -67,6 +67,7 @@ struct sce_plan {
   float *part_enc, *part_dec, *db_part, *bnorm, *l1_over_b, *loss_stage, *nnz_stage;
   int tiles_mB_max;
   std::map<int, BatchMaps*>* maps;
+  int pair_encode, pair_decode, pair_dcode, pair_dw;  // 1: run that GEMM on CTA pairs (cta_group::2, 256-row tiles)
   int bk_encode, bk_decode, bk_dcode;  // K block (64: 128-byte swizzle, 32: 64-byte swizzle) of the K-major GEMMs
   int last_launches;
   long long step;  // number of optimiser steps taken
@@ -174,6 +175,8 @@ static size_t carve(sce_plan* p, const sce_desc& d, uint8_t* base) {
 // tensor maps for one batch size
 // ------------------------------------------------------------------------------------------------
 static int bn_for(int N) { return N > 128 ? 256 : 128; }
+// a CTA pair needs at least two 128-row blocks of output
+static bool use_pair(int flag, int rows) { return flag && rows > kBM; }
 constexpr int kBkDw = 32;  // K block of the MN-major weight-gradient GEMM
 // K block of the GEMMs with K-major operands: 32 (64-byte swizzle, 4 stages of 48 KB at BN = 256) keeps three
 // stages in flight behind the one being multiplied; 64 (128-byte swizzle) only has room for two stages.
@@ -185,6 +188,10 @@ static int tune_bk(const char* env, int dflt) {
   if (!v) return dflt;
   const int k = atoi(v);
   return (k == 32 || k == 64) ? k : dflt;
+}
+static int tune_flag(const char* env, int dflt) {
+  const char* v = getenv(env);
+  return v ? (atoi(v) != 0) : dflt;
 }
 static CUtensorMapSwizzle swizzle_for_bk(int bk) {
   return bk == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
@@ -228,13 +235,16 @@ static int build_maps(sce_plan* p, int B, BatchMaps** out) {
   bool ok = true;
   // encode: A = x [xm,B,d] K-major, B = Wenc [M,n,d] K-major
   ok &= actk(&m->encode.a_hi[0], &m->encode.a_lo[0], p->x_hi, p->x_lo, xm, dd, p->bk_encode);
-  ok &= map2(&m->encode.b_hi[0], &m->encode.b_lo[0], p->wenc_hi, p->wenc_lo, M, n, dd, bn_for(d.n), p->bk_encode);
+  // (K-major B tiles are loaded whole by a single CTA, in halves by the two CTAs of a pair)
+  ok &= map2(&m->encode.b_hi[0], &m->encode.b_lo[0], p->wenc_hi, p->wenc_lo, M, n, dd,
+             bn_for(d.n) / (use_pair(p->pair_encode, B) ? 2 : 1), p->bk_encode);
   // decode: A = c [M,B,n] K-major, B = Wdec [M,n,d] MN-major (box = 64 k-rows x 64 columns)
   ok &= actk(&m->decode.a_hi[0], &m->decode.a_lo[0], p->c_hi, p->c_lo, M, n, p->bk_decode);
   ok &= map2(&m->decode.b_hi[0], &m->decode.b_lo[0], p->wdec_hi, p->wdec_lo, M, n, dd, p->bk_decode, 0);
   // dcode: A = g [M,B,d] K-major, B = Wdec K-major
   ok &= actk(&m->dcode.a_hi[0], &m->dcode.a_lo[0], p->g_hi, p->g_lo, M, dd, p->bk_dcode);
-  ok &= map2(&m->dcode.b_hi[0], &m->dcode.b_lo[0], p->wdec_hi, p->wdec_lo, M, n, dd, bn_for(d.n), p->bk_dcode);
+  ok &= map2(&m->dcode.b_hi[0], &m->dcode.b_lo[0], p->wdec_hi, p->wdec_lo, M, n, dd,
+             bn_for(d.n) / (use_pair(p->pair_dcode, B) ? 2 : 1), p->bk_dcode);
   // weight gradients: everything MN-major, reduction over the batch rows
   if (d.variant == SCE_UNTIED) {
     ok &= act(&m->dw_enc.a_hi[0], &m->dw_enc.a_lo[0], p->dz_hi, p->dz_lo, M, n, kBkDw);
@@ -263,12 +273,12 @@ static int build_maps(sce_plan* p, int B, BatchMaps** out) {
 // ------------------------------------------------------------------------------------------------
 // GEMM launcher
 // ------------------------------------------------------------------------------------------------
-template <class Epi, int BN, int BK, bool A_MN, bool B_MN, int STAGES, bool SPLIT_ACC = false>
+template <class Epi, int BN, int BK, bool A_MN, bool B_MN, int STAGES, bool SPLIT_ACC = false, bool CTA2 = false>
 static int launch_gemm_t(const sce_plan* p, const GemmMaps& maps, int nsets, const int* a_batched,
                          const int* b_batched, int k_total, int passes, int m_total, int n_total,
                          const typename Epi::Params& epi, cudaStream_t st) {
-  using SM = GemmSmem<BN, BK, A_MN, B_MN, STAGES, Epi::kWarpStageBytes>;
-  auto kern = gemm_split_kernel<Epi, BN, BK, A_MN, B_MN, STAGES, SPLIT_ACC>;
+  using SM = GemmSmem<BN, BK, A_MN, B_MN, STAGES, Epi::kWarpStageBytes, CTA2>;
+  auto kern = gemm_split_kernel<Epi, BN, BK, A_MN, B_MN, STAGES, SPLIT_ACC, CTA2>;
   static bool configured = false;
   if (!configured) {
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kBytes));
@@ -290,22 +300,45 @@ static int launch_gemm_t(const sce_plan* p, const GemmMaps& maps, int nsets, con
   gp.n_models = p->d.n_models;
   gp.m_total = m_total;
   gp.n_total = n_total;
-  gp.tiles_m = (m_total + kBM - 1) / kBM;
+  constexpr int kTileRows = CTA2 ? 2 * kBM : kBM;   // a CTA pair owns 256-row tiles
+  gp.tiles_m = (m_total + kTileRows - 1) / kTileRows;
   gp.tiles_n = (n_total + BN - 1) / BN;
   gp.epi = epi;
   const int tiles = gp.n_models * gp.tiles_m * gp.tiles_n;
-  const int grid = tiles < p->sms ? tiles : p->sms;
-  kern<<<grid, kGemmThreads, SM::kBytes, st>>>(gp);
-  CUDA_TRY(cudaGetLastError());
+  const int units = CTA2 ? p->sms / 2 : p->sms;     // persistent: one CTA (or CTA pair) per SM (pair)
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((tiles < units ? tiles : units) * (CTA2 ? 2 : 1));
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = SM::kBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CTA2 ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, gp));
   return SCE_OK;
 }
 
-// Dispatch a K-major-A GEMM on (output width -> BN, plan BK): BN 256/128 x BK 64/32 with 2/4 resp. 3/6 stages.
-#define SCE_LAUNCH_K(EPI, B_MN, SPLIT, WIDE, BK, ...)                                                         \
-  ((WIDE) ? ((BK) == 32 ? launch_gemm_t<EPI, 256, 32, false, B_MN, 4, SPLIT>(__VA_ARGS__)                      \
-                        : launch_gemm_t<EPI, 256, 64, false, B_MN, 2, SPLIT>(__VA_ARGS__))                     \
-          : ((BK) == 32 ? launch_gemm_t<EPI, 128, 32, false, B_MN, 6, SPLIT>(__VA_ARGS__)                      \
-                        : launch_gemm_t<EPI, 128, 64, false, B_MN, 3, SPLIT>(__VA_ARGS__)))
+// Dispatch a K-major-A GEMM on (output width -> BN, K block, single CTA or CTA pair). Stage counts fill the
+// 192 KB operand ring: single 256x{64,32} -> 2,4; 128x{64,32} -> 3,6; pair 256x{64,32} -> 3,6; 128x{64,32} -> 4,8.
+template <class Epi, bool B_MN, bool SPLIT, class... Args>
+static int launch_k(bool wide, int bk, bool pair, Args&&... a) {
+  if (wide) {
+    if (bk == 32)
+      return pair ? launch_gemm_t<Epi, 256, 32, false, B_MN, 6, SPLIT, true>(a...)
+                  : launch_gemm_t<Epi, 256, 32, false, B_MN, 4, SPLIT, false>(a...);
+    return pair ? launch_gemm_t<Epi, 256, 64, false, B_MN, 3, SPLIT, true>(a...)
+                : launch_gemm_t<Epi, 256, 64, false, B_MN, 2, SPLIT, false>(a...);
+  }
+  if (bk == 32)
+    return pair ? launch_gemm_t<Epi, 128, 32, false, B_MN, 8, SPLIT, true>(a...)
+                : launch_gemm_t<Epi, 128, 32, false, B_MN, 6, SPLIT, false>(a...);
+  return pair ? launch_gemm_t<Epi, 128, 64, false, B_MN, 4, SPLIT, true>(a...)
+              : launch_gemm_t<Epi, 128, 64, false, B_MN, 3, SPLIT, false>(a...);
+}
 
 // ------------------------------------------------------------------------------------------------
 // helpers shared by step / forward / grads
@@ -385,8 +418,8 @@ static int run_pipeline(sce_plan* p, const float* x, int B, float* x_hat, bool b
     ep.tiles_m = tiles_mB;
     ep.flag_zero = 1;
     ep.tiles_n = n > 128 ? (n + 255) / 256 : 1;
-    rc = SCE_LAUNCH_K(EpiEncode, false, false, n > 128, p->bk_encode, p, maps->encode, 1, xb, one, dd, d.fwd_passes, B, n,
-                      ep, st);
+    rc = launch_k<EpiEncode, false, false>(n > 128, p->bk_encode, use_pair(p->pair_encode, B), p, maps->encode, 1, xb, one,
+                                           dd, d.fwd_passes, B, n, ep, st);
     if (rc) return rc;
     ++launches;
     n_enc_parts = tiles_mB * 8 * ep.tiles_n;
@@ -396,8 +429,8 @@ static int run_pipeline(sce_plan* p, const float* x, int B, float* x_hat, bool b
     sp.out = reinterpret_cast<float*>(p->dz_hi);
     sp.model_stride = Bm * n;
     sp.ld = n;
-    rc = SCE_LAUNCH_K(EpiStoreF32, false, false, n > 128, p->bk_encode, p, maps->encode, 1, xb, one, dd, d.fwd_passes, B,
-                      n, sp, st);
+    rc = launch_k<EpiStoreF32, false, false>(n > 128, p->bk_encode, use_pair(p->pair_encode, B), p, maps->encode, 1, xb,
+                                             one, dd, d.fwd_passes, B, n, sp, st);
     if (rc) return rc;
     ++launches;
     if ((size_t)n * 4 > 200 * 1024) return fail(SCE_ERR_INVALID, "top-k: n = %d exceeds the shared-memory row buffer", n);
@@ -432,8 +465,8 @@ static int run_pipeline(sce_plan* p, const float* x, int B, float* x_hat, bool b
   dp.tiles_m = tiles_mB;
   dp.gscale = 2.0f / ((float)B * (float)dd);
   dp.tiles_n = dd > 128 ? (dd + 255) / 256 : 1;
-  rc = SCE_LAUNCH_K(EpiDecode, true, true, dd > 128, p->bk_decode, p, maps->decode, 1, one, one, n, d.fwd_passes, B, dd, dp,
-                    st);
+  rc = launch_k<EpiDecode, true, true>(dd > 128, p->bk_decode, use_pair(p->pair_decode, B), p, maps->decode, 1, one, one, n,
+                                       d.fwd_passes, B, dd, dp, st);
   if (rc) return rc;
   ++launches;
 
@@ -460,8 +493,8 @@ static int run_pipeline(sce_plan* p, const float* x, int B, float* x_hat, bool b
     zp.c_model_stride = Bm * n;
     zp.ldc = n;
     zp.tiles_m = tiles_mB;
-    rc = SCE_LAUNCH_K(EpiDcode, false, false, n > 128, p->bk_dcode, p, maps->dcode, 1, one, one, dd, d.bwd_passes, B, n, zp,
-                      st);
+    rc = launch_k<EpiDcode, false, false>(n > 128, p->bk_dcode, use_pair(p->pair_dcode, B), p, maps->dcode, 1, one, one, dd,
+                                          d.bwd_passes, B, n, zp, st);
     if (rc) return rc;
     ++launches;
 
@@ -472,9 +505,12 @@ static int run_pipeline(sce_plan* p, const float* x, int B, float* x_hat, bool b
       sp.out = out;
       sp.model_stride = (long long)n * dd;
       sp.ld = dd;
+      const bool pair = use_pair(p->pair_dw, n);
       if (dd > 128)
-        return launch_gemm_t<EpiStoreF32, 256, kBkDw, true, true, 4, true>(p, gm, nsets, ab, bb, B, d.bwd_passes, n, dd, sp, st);
-      return launch_gemm_t<EpiStoreF32, 128, kBkDw, true, true, 6, true>(p, gm, nsets, ab, bb, B, d.bwd_passes, n, dd, sp, st);
+        return pair ? launch_gemm_t<EpiStoreF32, 256, kBkDw, true, true, 6, true, true>(p, gm, nsets, ab, bb, B, d.bwd_passes, n, dd, sp, st)
+                    : launch_gemm_t<EpiStoreF32, 256, kBkDw, true, true, 4, true, false>(p, gm, nsets, ab, bb, B, d.bwd_passes, n, dd, sp, st);
+      return pair ? launch_gemm_t<EpiStoreF32, 128, kBkDw, true, true, 8, true, true>(p, gm, nsets, ab, bb, B, d.bwd_passes, n, dd, sp, st)
+                  : launch_gemm_t<EpiStoreF32, 128, kBkDw, true, true, 6, true, false>(p, gm, nsets, ab, bb, B, d.bwd_passes, n, dd, sp, st);
     };
     if (d.variant == SCE_UNTIED) {
       rc = dw(maps->dw_enc, 1, one, xb, p->dw_enc);
@@ -538,6 +574,12 @@ int sce_plan_create(const sce_desc* desc, const sce_buffers* buffers, sce_plan**
   p->b = b;
   p->sms = sms;
   p->xm = desc->x_per_model ? desc->n_models : 1;
+  // CTA pairs by default for all four GEMMs (same-box A/B in profiles/r01g_pair_tuning.txt: -10 % encode,
+  // -9 % decode, -3 % dcode, -21 % weight gradient on that box; env SCE_TUNE_PAIR_* = 0 switches one back)
+  p->pair_encode = tune_flag("SCE_TUNE_PAIR_ENCODE", 1);
+  p->pair_decode = tune_flag("SCE_TUNE_PAIR_DECODE", 1);
+  p->pair_dcode = tune_flag("SCE_TUNE_PAIR_DCODE", 1);
+  p->pair_dw = tune_flag("SCE_TUNE_PAIR_DW", 1);
   p->bk_encode = tune_bk("SCE_TUNE_BK_ENCODE", 64);
   p->bk_decode = tune_bk("SCE_TUNE_BK_DECODE", 32);
   p->bk_dcode = tune_bk("SCE_TUNE_BK_DCODE", 64);

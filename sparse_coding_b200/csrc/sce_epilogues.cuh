@@ -162,7 +162,7 @@ struct EpiEncode {
   __device__ __forceinline__ void finish() {
     if (T.lane == 0) tma_store_wait_read();  // the staging tiles must outlive their bulk stores
     const float a = warp_sum(l1), b = warp_sum(float(nnz));
-    if (T.lane == 0) {
+    if (T.lane == 0 && T.m_blk * kBM < m_total) {  // (a CTA pair's second half may lie wholly past the batch)
       float* o = P.part +
                  ((((long long)T.model * P.tiles_m + T.m_blk) * 8 + T.grp * 4 + T.warp_q) * P.tiles_n + T.n_blk) * 2;
       o[0] = a;
@@ -222,7 +222,7 @@ struct EpiDecode {
   }
   __device__ __forceinline__ void finish() {
     const float a = warp_sum(sq);
-    if (T.lane == 0)
+    if (T.lane == 0 && T.m_blk * kBM < m_total)
       P.part[(((long long)T.model * P.tiles_m + T.m_blk) * 8 + T.grp * 4 + T.warp_q) * P.tiles_n + T.n_blk] = a;
   }
 };
@@ -283,7 +283,7 @@ struct EpiDcode {
       split2(v0, v1, whi[j >> 1], wlo[j >> 1]);
     }
     stage_and_store(stage, T.lane, whi, wlo, &P.out_hi, &P.out_lo, col, T.m_blk * kBM + T.warp_q * 32, T.model);
-    if (P.db_part) {
+    if (P.db_part && T.m_blk * kBM < m_total) {  // warp-uniform
       // transpose-reduce: 32 lanes x 32 columns -> lane j holds the sum of column j (31 shuffles)
 #pragma unroll
       for (int half = 16; half >= 1; half >>= 1) {

@@ -48,10 +48,11 @@ struct GemmParams {
   EpiParams epi;
 };
 
-template <int BN, int BK, bool A_MN, bool B_MN, int STAGES, int EPI_WARP_BYTES = 0>
+template <int BN, int BK, bool A_MN, bool B_MN, int STAGES, int EPI_WARP_BYTES = 0, bool CTA2 = false>
 struct GemmSmem {
   static constexpr int kATile = kBM * BK * 2;   // bytes, one of hi/lo
-  static constexpr int kBTile = BN * BK * 2;
+  static constexpr int kBRows = CTA2 ? BN / 2 : BN;  // a CTA pair splits the B tile between its two CTAs
+  static constexpr int kBTile = kBRows * BK * 2;
   static constexpr int kStage = 2 * kATile + 2 * kBTile;
   static constexpr int kBarOff = STAGES * kStage;
   static constexpr int kEpiOff = kBarOff + 1024;  // barriers + tmem ptr live in the 1 KB before (keeps 1 KB alignment)
@@ -68,14 +69,20 @@ struct GemmSmem {
 // chain); the cross terms are 2^-8 of the total, so moving them out shortens the chain that matters 3x.
 // Costs the second accumulator stage (tile epilogue no longer overlaps the next main loop), so it is used
 // where the reduction is long and the epilogue short: the decode GEMM (K = n).
-template <class Epi, int BN, int BK, bool A_MN, bool B_MN, int STAGES, bool SPLIT_ACC = false>
+//
+// CTA2: the tile is 256 x BN and is computed by a CTA pair (cluster of 2, tcgen05 cta_group::2). Each CTA
+// keeps 128 accumulator rows in its own TMEM, loads its own 128 rows of A and HALF of the B tile, so a stage
+// is 1/3 smaller (three K=64 stages fit instead of two) and each SM reads a third less shared memory per
+// MMA. `tiles_m` then counts 256-row tiles; TileCoord::m_blk stays in 128-row units (2*tile_m + cta rank).
+template <class Epi, int BN, int BK, bool A_MN, bool B_MN, int STAGES, bool SPLIT_ACC = false, bool CTA2 = false>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_split_kernel(const __grid_constant__ GemmParams<typename Epi::Params> p) {
   static_assert(BN % 64 == 0 && BN <= 256, "BN must be a multiple of 64, at most 256");
   static_assert(BK % 16 == 0 && BK <= 64, "BK in {16,32,48,64}");
   static_assert(A_MN || BK == 64 || BK == 32, "K-major A: one swizzled row per tile row, 128 B (BK=64) or 64 B (BK=32)");
   static_assert(B_MN || BK == 64 || BK == 32, "K-major B: one swizzled row per tile row, 128 B (BK=64) or 64 B (BK=32)");
-  using SM = GemmSmem<BN, BK, A_MN, B_MN, STAGES, Epi::kWarpStageBytes>;
+  using SM = GemmSmem<BN, BK, A_MN, B_MN, STAGES, Epi::kWarpStageBytes, CTA2>;
+  static_assert(!CTA2 || BN % 128 == 0, "a CTA pair splits B in halves of whole 64-column boxes");
   constexpr int EC = Epi::kCols;  // accumulator columns handed to the epilogue per call (32 or 64)
   static_assert(EC == 32 || EC == 64, "epilogue chunk is 32 or 64 columns");
   static_assert(BN % EC == 0, "tile width must be a multiple of the epilogue chunk");
@@ -94,6 +101,9 @@ gemm_split_kernel(const __grid_constant__ GemmParams<typename Epi::Params> p) {
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int cta_rank = CTA2 ? int(cluster_ctarank()) : 0;
+  const int tile0 = CTA2 ? int(blockIdx.x >> 1) : int(blockIdx.x);       // first tile of this CTA (pair)
+  const int tile_step = CTA2 ? int(gridDim.x >> 1) : int(gridDim.x);
   const int num_tiles = p.n_models * p.tiles_m * p.tiles_n;
   const int kblocks = (p.k_total + BK - 1) / BK;
   const bool three = p.passes >= 3;
@@ -115,16 +125,22 @@ gemm_split_kernel(const __grid_constant__ GemmParams<typename Epi::Params> p) {
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], kEpiWarps);
+      mbar_init(&tempty_bar[s], CTA2 ? 2 * kEpiWarps : kEpiWarps);  // pair: both CTAs' epilogues report to CTA 0
     }
     fence_mbar_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_ptr, kTmemCols);
-    tmem_relinquish();
+    if constexpr (CTA2) {
+      tmem_alloc_2cta(tmem_ptr, kTmemCols);
+      tmem_relinquish_2cta();
+    } else {
+      tmem_alloc(tmem_ptr, kTmemCols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CTA2) cluster_sync_all();  // the peer's barriers must be initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
@@ -132,13 +148,20 @@ gemm_split_kernel(const __grid_constant__ GemmParams<typename Epi::Params> p) {
     // ======================= TMA producer =======================
     if (lane == 0) {
       const uint32_t stage_bytes = three ? uint32_t(SM::kStage) : uint32_t(SM::kATile + SM::kBTile);
+      // one copy: same-CTA barrier, or (pair) the cta_group::2 form that completes on CTA 0's barrier
+      auto load = [&](void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
+        if constexpr (CTA2) tma_load_3d_2cta(dst, m, bar, c0, c1, c2);
+        else tma_load_3d(dst, m, bar, c0, c1, c2);
+      };
+      constexpr int kBHalf = SM::kBRows;  // B rows (N index) this CTA loads
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < num_tiles; tile += tile_step) {
         const int model = tile / (p.tiles_m * p.tiles_n);
         const int rem = tile - model * (p.tiles_m * p.tiles_n);
-        const int m_blk = rem / p.tiles_n;
-        const int n_blk = rem - m_blk * p.tiles_n;
+        const int m_blk = (rem / p.tiles_n) * (CTA2 ? 2 : 1) + cta_rank;
+        const int n_blk = rem % p.tiles_n;
+        const int b_row0 = n_blk * BN + cta_rank * kBHalf;
         for (int set = 0; set < p.nsets; ++set) {
           const int am = p.a_batched[set] ? model : 0;
           const int bm = p.b_batched[set] ? model : 0;
@@ -148,32 +171,27 @@ gemm_split_kernel(const __grid_constant__ GemmParams<typename Epi::Params> p) {
             uint8_t* sa_lo = sa_hi + SM::kATile;
             uint8_t* sb_hi = sa_lo + SM::kATile;
             uint8_t* sb_lo = sb_hi + SM::kBTile;
-            mbar_expect_tx(&full_bar[stage], stage_bytes);
+            // pair: CTA 0 announces the bytes of BOTH CTAs; the peer's copies complete on CTA 0's barrier
+            if (!CTA2 || cta_rank == 0) mbar_expect_tx(&full_bar[stage], CTA2 ? 2 * stage_bytes : stage_bytes);
             const int k0 = kb * BK;
             if constexpr (!A_MN) {
-              tma_load_3d(sa_hi, &p.a_hi[set], &full_bar[stage], k0, m_blk * kBM, am);
-              if (three) tma_load_3d(sa_lo, &p.a_lo[set], &full_bar[stage], k0, m_blk * kBM, am);
+              load(sa_hi, &p.a_hi[set], &full_bar[stage], k0, m_blk * kBM, am);
+              if (three) load(sa_lo, &p.a_lo[set], &full_bar[stage], k0, m_blk * kBM, am);
             } else {
 #pragma unroll
               for (int j = 0; j < kBM / 64; ++j) {
-                tma_load_3d(sa_hi + j * (BK * 128), &p.a_hi[set], &full_bar[stage],
-                            m_blk * kBM + j * 64, k0, am);
-                if (three)
-                  tma_load_3d(sa_lo + j * (BK * 128), &p.a_lo[set], &full_bar[stage],
-                              m_blk * kBM + j * 64, k0, am);
+                load(sa_hi + j * (BK * 128), &p.a_hi[set], &full_bar[stage], m_blk * kBM + j * 64, k0, am);
+                if (three) load(sa_lo + j * (BK * 128), &p.a_lo[set], &full_bar[stage], m_blk * kBM + j * 64, k0, am);
               }
             }
             if constexpr (!B_MN) {
-              tma_load_3d(sb_hi, &p.b_hi[set], &full_bar[stage], k0, n_blk * BN, bm);
-              if (three) tma_load_3d(sb_lo, &p.b_lo[set], &full_bar[stage], k0, n_blk * BN, bm);
+              load(sb_hi, &p.b_hi[set], &full_bar[stage], k0, b_row0, bm);
+              if (three) load(sb_lo, &p.b_lo[set], &full_bar[stage], k0, b_row0, bm);
             } else {
 #pragma unroll
-              for (int j = 0; j < BN / 64; ++j) {
-                tma_load_3d(sb_hi + j * (BK * 128), &p.b_hi[set], &full_bar[stage],
-                            n_blk * BN + j * 64, k0, bm);
-                if (three)
-                  tma_load_3d(sb_lo + j * (BK * 128), &p.b_lo[set], &full_bar[stage],
-                              n_blk * BN + j * 64, k0, bm);
+              for (int j = 0; j < kBHalf / 64; ++j) {
+                load(sb_hi + j * (BK * 128), &p.b_hi[set], &full_bar[stage], b_row0 + j * 64, k0, bm);
+                if (three) load(sb_lo + j * (BK * 128), &p.b_lo[set], &full_bar[stage], b_row0 + j * 64, k0, bm);
               }
             }
             if (++stage == STAGES) {
@@ -186,8 +204,16 @@ gemm_split_kernel(const __grid_constant__ GemmParams<typename Epi::Params> p) {
     }
   } else if (warp == 1) {
     // ======================= MMA issuer =======================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(kBM, BN, A_MN, B_MN);
+    if (lane == 0 && cta_rank == 0) {  // in a pair only CTA 0 issues; its MMAs drive both SMs
+      constexpr uint32_t idesc = make_idesc_bf16(CTA2 ? 2 * kBM : kBM, BN, A_MN, B_MN);
+      auto mma = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t acc_flag) {
+        if constexpr (CTA2) umma_bf16_2cta(d, a, b, idesc, acc_flag);
+        else umma_bf16(d, a, b, idesc, acc_flag);
+      };
+      auto commit = [&](uint64_t* bar) {
+        if constexpr (CTA2) umma_commit_2cta(bar);
+        else umma_commit(bar);
+      };
       constexpr uint32_t a_lbo = A_MN ? BK * 128 : 16;
       constexpr uint32_t b_lbo = B_MN ? BK * 128 : 16;
       constexpr uint32_t a_kstep = A_MN ? 2048 : 32;  // bytes per K=16 slice
@@ -199,7 +225,7 @@ gemm_split_kernel(const __grid_constant__ GemmParams<typename Epi::Params> p) {
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < num_tiles; tile += tile_step) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + uint32_t(acc * BN);
@@ -220,21 +246,21 @@ gemm_split_kernel(const __grid_constant__ GemmParams<typename Epi::Params> p) {
               const uint64_t al = make_sdesc(sa_lo + k * a_kstep, a_lbo, a_sbo, a_lt);
               const uint64_t bl = make_sdesc(sb_lo + k * b_kstep, b_lbo, b_sbo, b_lt);
               // small cross terms first, then the dominant hi*hi term
-              umma_bf16(d_cross, al, bh, idesc, accumulate);
-              umma_bf16(d_cross, ah, bl, idesc, 1);
-              umma_bf16(d_tmem, ah, bh, idesc, SPLIT_ACC ? accumulate : 1u);
+              mma(d_cross, al, bh, accumulate);
+              mma(d_cross, ah, bl, 1);
+              mma(d_tmem, ah, bh, SPLIT_ACC ? accumulate : 1u);
             } else {
-              umma_bf16(d_tmem, ah, bh, idesc, accumulate);
+              mma(d_tmem, ah, bh, accumulate);
             }
             accumulate = 1;
           }
-          umma_commit(&empty_bar[stage]);  // smem slot is free once these MMAs have read it
+          commit(&empty_bar[stage]);  // smem slot is free (in both CTAs of a pair) once these MMAs have read it
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+        commit(&tfull_bar[acc]);  // accumulator complete -> epilogue (of both CTAs)
         if (++acc == kAccStages) {
           acc = 0;
           acc_phase ^= 1;
@@ -247,12 +273,12 @@ gemm_split_kernel(const __grid_constant__ GemmParams<typename Epi::Params> p) {
     const int grp = (warp - 4) >> 2;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = tile0; tile < num_tiles; tile += tile_step) {
       TileCoord tc;
       tc.model = tile / (p.tiles_m * p.tiles_n);
       const int rem = tile - tc.model * (p.tiles_m * p.tiles_n);
-      tc.m_blk = rem / p.tiles_n;
-      tc.n_blk = rem - tc.m_blk * p.tiles_n;
+      tc.m_blk = (rem / p.tiles_n) * (CTA2 ? 2 : 1) + cta_rank;
+      tc.n_blk = rem % p.tiles_n;
       tc.row = tc.m_blk * kBM + wq * 32 + lane;
       tc.col0 = tc.n_blk * BN;
       tc.warp_q = wq;
@@ -285,7 +311,10 @@ gemm_split_kernel(const __grid_constant__ GemmParams<typename Epi::Params> p) {
           // all TMEM reads of this accumulator are done: hand it back to the MMA warp early
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+          if (lane == 0) {
+            if constexpr (CTA2) mbar_arrive_cta0(&tempty_bar[acc]);
+            else mbar_arrive(&tempty_bar[acc]);
+          }
         }
         epi.chunk(c * EC, r);
       }
@@ -299,9 +328,11 @@ gemm_split_kernel(const __grid_constant__ GemmParams<typename Epi::Params> p) {
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (CTA2) cluster_sync_all();  // neither CTA may free TMEM / exit while the pair's MMAs or signals are in flight
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    if constexpr (CTA2) tmem_dealloc_2cta(tmem_base, kTmemCols);
+    else tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 

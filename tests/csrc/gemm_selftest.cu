@@ -91,7 +91,7 @@ static bool tmaps(const Operand& o, uint32_t box_rows_kmajor, int BK, CUtensorMa
          make_tmap_bf16(lo, o.s.d_lo, o.models, o.K, o.rows, o.rows, (uint64_t)o.rows * o.K, BK);
 }
 
-template <int BN, int BK, bool A_MN, bool B_MN, int STAGES>
+template <int BN, int BK, bool A_MN, bool B_MN, int STAGES, bool SPLIT = false, bool CTA2 = false>
 static bool run_case(const char* name, int models, int M, int N, int K, int nsets, int passes,
                      bool a_shared, bool b_shared) {
   Operand A[2], B[2];
@@ -107,7 +107,8 @@ static bool run_case(const char* name, int models, int M, int N, int K, int nset
   GemmParams<EpiStoreF32::Params> p;
   memset(&p, 0, sizeof(p));
   for (int s = 0; s < nsets; ++s) {
-    if (!tmaps(A[s], kBM, BK, &p.a_hi[s], &p.a_lo[s]) || !tmaps(B[s], BN, BK, &p.b_hi[s], &p.b_lo[s])) {
+    if (!tmaps(A[s], kBM, BK, &p.a_hi[s], &p.a_lo[s]) ||
+        !tmaps(B[s], CTA2 ? BN / 2 : BN, BK, &p.b_hi[s], &p.b_lo[s])) {
       printf("[%s] tensor map encode failed\n", name);
       return false;
     }
@@ -120,24 +121,40 @@ static bool run_case(const char* name, int models, int M, int N, int K, int nset
   p.n_models = models;
   p.m_total = M;
   p.n_total = N;
-  p.tiles_m = (M + kBM - 1) / kBM;
+  const int tile_rows = CTA2 ? 2 * kBM : kBM;
+  p.tiles_m = (M + tile_rows - 1) / tile_rows;
   p.tiles_n = (N + BN - 1) / BN;
   p.epi.out = d_out;
   p.epi.model_stride = (long long)M * N;
   p.epi.ld = N;
 
-  using SM = GemmSmem<BN, BK, A_MN, B_MN, STAGES>;
-  auto kern = gemm_split_kernel<EpiStoreF32, BN, BK, A_MN, B_MN, STAGES>;
+  using SM = GemmSmem<BN, BK, A_MN, B_MN, STAGES, 0, CTA2>;
+  auto kern = gemm_split_kernel<EpiStoreF32, BN, BK, A_MN, B_MN, STAGES, SPLIT, CTA2>;
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kBytes));
   int sms = 0;
   CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
   int tiles = models * p.tiles_m * p.tiles_n;
-  int grid = tiles < sms ? tiles : sms;
+  const int units = CTA2 ? sms / 2 : sms;
+  int grid = (tiles < units ? tiles : units) * (CTA2 ? 2 : 1);
   cudaEvent_t e0, e1;
   CK(cudaEventCreate(&e0));
   CK(cudaEventCreate(&e1));
   CK(cudaEventRecord(e0));
-  kern<<<grid, kGemmThreads, SM::kBytes>>>(p);
+  {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = SM::kBytes;
+    cfg.stream = 0;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CTA2 ? 2 : 1;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    CK(cudaLaunchKernelEx(&cfg, kern, p));
+  }
   CK(cudaEventRecord(e1));
   cudaError_t err = cudaDeviceSynchronize();
   if (err != cudaSuccess) {
@@ -246,6 +263,17 @@ int main(int argc, char** argv) {
   ok &= run_case<128, 32, false, false, 6>("kk32_bn128", 2, 256, 384, 256, 1, 3, true, false);
   ok &= run_case<256, 32, false, true, 4>("kmn32_3pass", 2, 256, 512, 512, 1, 3, false, false);
   ok &= run_case<256, 32, false, true, 4>("kmn32_ragged", 2, 200, 328, 104, 1, 3, false, false);
+  // ---- CTA pairs (cta_group::2, 256-row tiles)
+  ok &= run_case<256, 64, false, false, 3, false, true>("pair_kk_k16", 1, 256, 256, 16, 1, 1, false, false);
+  ok &= run_case<256, 64, false, false, 3, false, true>("pair_kk_k64", 1, 256, 256, 64, 1, 1, false, false);
+  ok &= run_case<256, 64, false, false, 3, false, true>("pair_kk_multi", 3, 768, 512, 512, 1, 3, true, false);
+  ok &= run_case<256, 64, false, false, 3, false, true>("pair_kk_ragged", 2, 200, 328, 104, 1, 3, true, false);
+  ok &= run_case<256, 64, false, false, 3, false, true>("pair_kk_short", 2, 100, 328, 104, 1, 3, true, false);
+  ok &= run_case<128, 64, false, false, 4, false, true>("pair_kk_bn128", 2, 512, 384, 256, 1, 3, true, false);
+  ok &= run_case<256, 32, false, true, 6, true, true>("pair_kmn_split", 2, 512, 512, 512, 1, 3, false, false);
+  ok &= run_case<256, 32, false, true, 6, true, true>("pair_kmn_ragged", 2, 200, 328, 104, 1, 3, false, false);
+  ok &= run_case<256, 32, true, true, 6, true, true>("pair_mnmn_2set", 2, 512, 512, 320, 2, 3, false, true);
+  ok &= run_case<256, 32, true, true, 6, true, true>("pair_mnmn_ragged", 2, 200, 328, 104, 2, 3, false, true);
   // ---- K-major A x MN-major B (decode shape: X^ = C W)
   ok &= run_case<256, 64, false, true, 2>("kmn_k16", 1, 128, 256, 16, 1, 1, false, false);
   ok &= run_case<256, 64, false, true, 2>("kmn_k64", 1, 128, 256, 64, 1, 1, false, false);

@@ -1,0 +1,16 @@
+#!/bin/bash
+# A/B CTA-pair (cta_group::2) mode per GEMM inside ONE gpurun call. usage: tools/tune_pair.sh
+run() {
+  env "$@" timeout 300 python bench.py --steps 40 --warmup 5 --no-cpu-baseline 2>/dev/null | python -c "
+import json,sys; d=json.loads(sys.stdin.read()); p=d['phases_ms']
+print('%-70s step %.3f ms  enc %.3f dec %.3f dcode %.3f dw %.3f  sm %s MHz' % ('$*', d['ms_per_step'], p['encode'], p['decode'], p['dcode'], p['dw'], d['clocks']['sm_mhz']))"
+}
+run SCE_X=0
+run SCE_TUNE_PAIR_ENCODE=1
+run SCE_TUNE_PAIR_DECODE=1
+run SCE_TUNE_PAIR_DECODE=1 SCE_TUNE_BK_DECODE=64
+run SCE_TUNE_PAIR_DCODE=1
+run SCE_TUNE_PAIR_DW=1
+run SCE_TUNE_PAIR_ENCODE=1 SCE_TUNE_PAIR_DECODE=1 SCE_TUNE_PAIR_DCODE=1 SCE_TUNE_PAIR_DW=1
+run SCE_TUNE_PAIR_ENCODE=1 SCE_TUNE_PAIR_DECODE=1 SCE_TUNE_PAIR_DCODE=1 SCE_TUNE_PAIR_DW=1 SCE_TUNE_BK_DECODE=64
+run SCE_X=0
