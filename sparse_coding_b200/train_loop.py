@@ -147,47 +147,60 @@ def unstacked_to_learned_dicts(ensemble, args, ensemble_hyperparams, buffer_hype
 # activation-chunk streaming: {folder}/{i}.pt  (fp16 [N,d], activation_dataset.py:499-503)
 # ----------------------------------------------------------------------------------------------------------------
 class ChunkStreamer:
-    """Iterates over device-resident chunks. While the caller trains on chunk i, chunk i+1 is read from disk into a
-    pinned staging buffer and copied to its own HBM buffer on a side stream (two device buffers, ping-pong)."""
+    """Iterates over device-resident chunks. While the caller trains on chunk i, a background thread reads chunk
+    i+1 from disk into one of two pinned staging buffers and copies it to one of two HBM buffers on a side stream
+    (ping-pong; the copy waits for the compute that last read that HBM buffer). The training stream only waits on
+    the copy-complete event, so disk, host memcpy and H2D all overlap with the GPU work of the previous chunk."""
 
     def __init__(self, folder: str, order: Iterable[int], device, keep_dtype: bool = True):
+        from concurrent.futures import ThreadPoolExecutor
         self.folder, self.order, self.device = folder, list(order), torch.device(device)
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.keep_dtype = keep_dtype
         self.copy_stream = torch.cuda.Stream(self.device)
-        self._pinned = None
+        self._pool = ThreadPoolExecutor(max_workers=1)
+        self._pinned = [None, None]
         self._dev = [None, None]
+        self._copied = [None, None]     # event: H2D into slot finished (pinned buffer reusable, data visible)
+        self._released = [None, None]   # event on the training stream: work reading slot has been enqueued
 
     def _stage(self, slot: int, chunk_idx: int):
+        torch.cuda.set_device(self.device)
         t = torch.load(os.path.join(self.folder, f"{chunk_idx}.pt"), map_location="cpu")
         if not self.keep_dtype or t.dtype not in (torch.float16, torch.float32):
             t = t.float()
         t = t.contiguous()
-        if self._pinned is None or self._pinned.shape != t.shape or self._pinned.dtype != t.dtype:
-            self._pinned = torch.empty_like(t).pin_memory()
-        # the pinned buffer is reused: the previous async copy out of it must have finished
-        self.copy_stream.synchronize()
-        self._pinned.copy_(t)
+        if self._copied[slot] is not None:
+            self._copied[slot].synchronize()                  # previous copy out of this pinned buffer is done
+        if self._pinned[slot] is None or self._pinned[slot].shape != t.shape or self._pinned[slot].dtype != t.dtype:
+            self._pinned[slot] = torch.empty(t.shape, dtype=t.dtype).pin_memory()
+        self._pinned[slot].copy_(t)
         if self._dev[slot] is None or self._dev[slot].shape != t.shape or self._dev[slot].dtype != t.dtype:
             self._dev[slot] = torch.empty(t.shape, dtype=t.dtype, device=self.device)
         with torch.cuda.stream(self.copy_stream):
-            self._dev[slot].copy_(self._pinned, non_blocking=True)
+            if self._released[slot] is not None:
+                self.copy_stream.wait_event(self._released[slot])
+            self._dev[slot].copy_(self._pinned[slot], non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(self.copy_stream)
+        self._copied[slot] = ev
         return ev
 
     def __iter__(self):
         if not self.order:
             return
-        pending = self._stage(0, self.order[0])
+        fut = self._pool.submit(self._stage, 0, self.order[0])
         for i, chunk_idx in enumerate(self.order):
             slot = i & 1
-            torch.cuda.current_stream(self.device).wait_event(pending)
-            current = self._dev[slot]
+            ev = fut.result()
             if i + 1 < len(self.order):
-                # the other slot was last used two chunks ago; make the copy wait for the compute that read it
-                self.copy_stream.wait_stream(torch.cuda.current_stream(self.device))
-                pending = self._stage(slot ^ 1, self.order[i + 1])
-            yield chunk_idx, current
+                fut = self._pool.submit(self._stage, slot ^ 1, self.order[i + 1])   # prefetch in the background
+            torch.cuda.current_stream(self.device).wait_event(ev)
+            yield chunk_idx, self._dev[slot]
+            rel = torch.cuda.Event()
+            rel.record(torch.cuda.current_stream(self.device))
+            self._released[slot] = rel
 
 
 class _Counter:
@@ -227,9 +240,10 @@ def train_on_chunks(ensemble, args: dict, dataset_folder: str, output_folder: st
         for j, idx in enumerate(_batch_index_lists(sampler)):
             batch = gather_rows(chunk, idx.to(device, non_blocking=True), sub=means)
             ensemble.step_batch(batch)
-        learned_dicts = unstacked_to_learned_dicts(ensemble, args, ensemble_hyperparams, buffer_hyperparams)
         last = i == len(chunk_order) - 1
         if last or (save_schedule == "sweep" and (i + 1) in [2 ** j for j in range(3, 10)]) or save_schedule == "every":
+            # export (a full D2H of the parameters, which also drains the GPU) only when a checkpoint is due
+            learned_dicts = unstacked_to_learned_dicts(ensemble, args, ensemble_hyperparams, buffer_hyperparams)
             it_folder = os.path.join(output_folder, f"_{i}")
             os.makedirs(it_folder, exist_ok=True)
             torch.save(learned_dicts, os.path.join(it_folder, "learned_dicts.pt"))
