@@ -194,19 +194,34 @@ struct EpiDecode {
   const TileCoord& T;
   int m_total, n_total;
   float sq = 0.f;
-  __device__ EpiDecode(const Params& p, const TileCoord& t, int m, int n, uint8_t*) : P(p), T(t), m_total(m), n_total(n) {}
+  float4 xn[8];  // the input row's next 32 columns, fetched one chunk ahead (hides the L2 latency of x behind
+                 // the tail of the main loop / the previous chunk; with SPLIT_ACC the epilogue is on the critical path)
+  __device__ __forceinline__ void fetch_x(int c) {
+    const int col = T.col0 + c;
+    const bool row_ok = T.row < m_total;
+    const float* x = P.x + (long long)T.model * P.x_model_stride + (long long)T.row * P.ld + col;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      xn[j] = (row_ok && col + 4 * j < n_total) ? __ldg(reinterpret_cast<const float4*>(x + 4 * j))
+                                               : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  __device__ EpiDecode(const Params& p, const TileCoord& t, int m, int n, uint8_t*) : P(p), T(t), m_total(m), n_total(n) {
+    fetch_x(T.grp * 32);
+  }
 
   __device__ __forceinline__ void chunk(int c, const uint32_t (&r)[32]) {
     const int col = T.col0 + c;
+    float4 xc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) xc[j] = xn[j];
+    fetch_x(c + 64);  // this warp's next chunk (harmless past the tile: predicated on n_total, unused)
     if (col >= n_total || T.row >= m_total) return;
-    const float* x = P.x + (long long)T.model * P.x_model_stride + (long long)T.row * P.ld + col;
     const long long off = (long long)T.model * P.g_model_stride + (long long)T.row * P.ld + col;
     uint32_t whi[16], wlo[16];
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
-      float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 xv = xc[j >> 2];
       const bool ok = col + j < n_total;  // d % 4 == 0
-      if (ok) xv = __ldg(reinterpret_cast<const float4*>(x + j));
       const float r0 = ok ? __uint_as_float(r[j]) - xv.x : 0.f, r1 = ok ? __uint_as_float(r[j + 1]) - xv.y : 0.f;
       const float r2 = ok ? __uint_as_float(r[j + 2]) - xv.z : 0.f, r3 = ok ? __uint_as_float(r[j + 3]) - xv.w : 0.f;
       sq += r0 * r0 + r1 * r1 + r2 * r2 + r3 * r3;
@@ -248,26 +263,34 @@ struct EpiDcode {
   int m_total, n_total;
   uint8_t* stage;
   float aB;
+  uint4 cn[4];  // the code row's next 32 columns (bf16), fetched one chunk ahead: c_hi streams from HBM
+  __device__ __forceinline__ void fetch_c(int c) {
+    const int col = T.col0 + c;
+    const bool row_ok = T.row < m_total;
+    const __nv_bfloat16* src = P.c_hi + (long long)T.model * P.c_model_stride + (long long)T.row * P.ldc + col;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      cn[j] = (row_ok && col + j * 8 < n_total) ? __ldg(reinterpret_cast<const uint4*>(src + j * 8))
+                                                : make_uint4(0, 0, 0, 0);
+  }
   __device__ EpiDcode(const Params& p, const TileCoord& t, int m, int n, uint8_t* st)
       : P(p), T(t), m_total(m), n_total(n), stage(st) {
     aB = __ldg(P.l1_over_b + T.model);
+    fetch_c(T.grp * 32);
   }
 
   __device__ __forceinline__ void chunk(int c, const uint32_t (&r)[32]) {
     const int col = T.col0 + c;
-    if (col >= n_total) return;  // warp-uniform
-    const bool row_ok = T.row < m_total;
-    const long long off = (long long)T.model * P.c_model_stride + (long long)T.row * P.ldc + col;
     uint32_t cw[16];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      uint4 v = make_uint4(0, 0, 0, 0);
-      if (row_ok && col + j * 8 < n_total) v = __ldg(reinterpret_cast<const uint4*>(P.c_hi + off + j * 8));
-      cw[4 * j] = v.x;
-      cw[4 * j + 1] = v.y;
-      cw[4 * j + 2] = v.z;
-      cw[4 * j + 3] = v.w;
+      cw[4 * j] = cn[j].x;
+      cw[4 * j + 1] = cn[j].y;
+      cw[4 * j + 2] = cn[j].z;
+      cw[4 * j + 3] = cn[j].w;
     }
+    fetch_c(c + 64);  // this warp's next chunk
+    if (col >= n_total) return;  // warp-uniform
     float dz[32];
     uint32_t whi[16], wlo[16];
 #pragma unroll
