@@ -35,6 +35,7 @@ WORKLOADS = {
     "cfg2": (16, 512, 4096, 8192, "16 TiedSAE d_model=512 dict_ratio=8 L1=logspace(-4,-2,16) batch=8192 (BASELINE configs[1])"),
     "cfg1": (1, 128, 256, 1024, "1 TiedSAE d_model=128 dict_ratio=2 L1=1e-3 batch=1024 (BASELINE configs[0])"),
     "cfg5": (1, 2048, 32768, 4096, "1 TiedSAE/GPU d_model=2048 dict_ratio=16 batch=4096 (BASELINE configs[4])"),
+    "cfg3": (12, 768, 6144, 8192, "12 TopK d_model=768 dict_ratio=8 k in {16,32,64} batch=8192 (one shape group of BASELINE configs[2])"),
 }
 METRIC = "activations/sec (whole job; rows consumed by every resident model)"
 
@@ -45,6 +46,8 @@ def l1_grid(M):
 
 def make_models(sig, M, d, n, seed):
     torch.manual_seed(seed)
+    if getattr(sig, "variant", None) == "topk":
+        return [sig.init(d, n, (16, 32, 64)[i % 3]) for i in range(M)]
     return [sig.init(d, n, a) for a in l1_grid(M)]
 
 
@@ -237,7 +240,8 @@ def main():
     K, W = args.steps, max(args.warmup, 3)
 
     # every rank owns its own shard of the sweep: same shapes, different seeds (model-axis sharding)
-    ens = S.FunctionalEnsemble(make_models(S.FunctionalTiedSAE, M, d, n, seed=rank), S.FunctionalTiedSAE, S.adam,
+    sig = S.TopKEncoder if args.workload == "cfg3" else S.FunctionalTiedSAE
+    ens = S.FunctionalEnsemble(make_models(sig, M, d, n, seed=rank), sig, S.adam,
                                {"lr": 1e-3}, device=dev, bwd_passes=args.bwd_passes)
     n_pool = 8
     host = synth_batches(n_pool, B, d, seed=1000, pin=True)        # identical stream on every rank
@@ -292,7 +296,7 @@ def main():
 
     # ---------------- informational: the same workload with single-pass bf16 backward GEMMs (NOT the headline)
     ms_alt = float("nan")
-    if world == 1 and args.bwd_passes == 3:
+    if world == 1 and args.bwd_passes == 3 and sig is S.FunctionalTiedSAE:
         del pool[4:]
         alt = S.FunctionalEnsemble(make_models(S.FunctionalTiedSAE, M, d, n, seed=rank), S.FunctionalTiedSAE, S.adam,
                                    {"lr": 1e-3}, device=dev, bwd_passes=1)

@@ -433,19 +433,16 @@ static int run_pipeline(sce_plan* p, const float* x, int B, float* x_hat, bool b
                                              one, dd, d.fwd_passes, B, n, sp, st);
     if (rc) return rc;
     ++launches;
-    if ((size_t)n * 4 > 200 * 1024) return fail(SCE_ERR_INVALID, "top-k: n = %d exceeds the shared-memory row buffer", n);
+    if ((size_t)n * 8 > 200 * 1024) return fail(SCE_ERR_INVALID, "top-k: n = %d exceeds the shared-memory row buffers", n);
     static bool cfg = false;
     if (!cfg) {
       CUDA_TRY(cudaFuncSetAttribute(topk_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       cfg = true;
     }
-    // scores/codes of model m live at m * batch_max * n; the kernel indexes with B, so launch per model
-    for (int m = 0; m < M; ++m) {
-      topk_select_kernel<<<dim3(B, 1), 256, (size_t)n * 4, st>>>(
-          reinterpret_cast<const float*>(p->dz_hi) + (long long)m * Bm * n, p->b.sparsity + m,
-          p->c_hi + (long long)m * Bm * n, p->c_lo + (long long)m * Bm * n, p->part_enc + (long long)m * B * 2, B, n);
-      ++launches;
-    }
+    // one block per (row, model); scores / codes of model m start at m * batch_max * n
+    topk_select_kernel<<<dim3(B, M), 256, (size_t)n * 8, st>>>(reinterpret_cast<const float*>(p->dz_hi), p->b.sparsity,
+                                                               p->c_hi, p->c_lo, p->part_enc, B, n, Bm * n);
+    ++launches;
     CUDA_TRY(cudaGetLastError());
     n_enc_parts = B;
   }

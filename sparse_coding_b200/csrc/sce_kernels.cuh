@@ -337,90 +337,209 @@ __device__ __forceinline__ uint32_t f2key(float f) {
   return (u & 0x80000000u) ? ~u : (u | 0x80000000u);  // ascending float order == ascending uint order
 }
 
+// warp-aggregated shared-memory histogram increment: lanes with the same bin elect one to add their count
+// (Gaussian-like scores share sign+exponent bits, so a naive atomicAdd serialises on two or three hot bins)
+__device__ __forceinline__ void hist_add(uint32_t* hist, uint32_t bin, bool active) {
+  const uint32_t act = __ballot_sync(0xffffffffu, active);
+  if (!active) return;
+  const uint32_t peers = __match_any_sync(act, bin);
+  if ((threadIdx.x & 31) == (__ffs(peers) - 1)) atomicAdd(&hist[bin], (uint32_t)__popc(peers));
+}
+
+// block-wide (256 threads, one per bin): find the bin holding the `rem`-th largest element by a parallel
+// suffix scan of the histogram (a serial walk by one thread costs ~250 dependent shared-memory reads per pass).
+// Updates sh_prefix / sh_remaining; ends with a __syncthreads().
+__device__ __forceinline__ void pick_bin(const uint32_t* hist, uint32_t* sh_prefix, uint32_t* sh_remaining,
+                                         uint32_t* warp_tot /*[8]*/, int shift, uint32_t* count_in_bin) {
+  const int r = threadIdx.x;            // reversed bin index: bin = 255 - r, so a PREFIX sum counts bins >= bin
+  const uint32_t h = hist[255 - r];
+  uint32_t p = h;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t v = __shfl_up_sync(0xffffffffu, p, o);
+    if ((r & 31) >= o) p += v;
+  }
+  if ((r & 31) == 31) warp_tot[r >> 5] = p;
+  __syncthreads();
+  uint32_t off = 0;
+  for (int w = 0; w < (r >> 5); ++w) off += warp_tot[w];
+  p += off;                              // elements in bins >= this one
+  const uint32_t rem = *sh_remaining;
+  __syncthreads();                       // everyone has read sh_remaining before the winner rewrites it
+  if (p >= rem && p - h < rem) {         // exactly one bin satisfies this (rem >= 1, total >= rem)
+    *sh_prefix |= uint32_t(255 - r) << shift;
+    *sh_remaining = rem - (p - h);
+    if (count_in_bin) *count_in_bin = h;
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ float key2relu(uint32_t key) {  // relu(float behind an order-preserving key)
+  return key > 0x80000000u ? __uint_as_float(key & 0x7FFFFFFFu) : 0.f;
+}
+
+// Rows are processed four elements per thread (n % 8 == 0 is guaranteed by the plan) with UNROLL independent
+// 16-byte loads in flight per thread: the first version (one 4-byte load per iteration) was latency-bound at
+// 1.1 TB/s (profiles: long-scoreboard stall 9.2 per issue).
 __global__ void __launch_bounds__(256) topk_select_kernel(const float* __restrict__ scores,
                                                           const long long* __restrict__ sparsity,
                                                           __nv_bfloat16* __restrict__ c_hi,
                                                           __nv_bfloat16* __restrict__ c_lo,
-                                                          float* __restrict__ part /*[M][B][2]*/, int B, int n) {
-  extern __shared__ uint32_t keys[];  // n keys
+                                                          float* __restrict__ part /*[M][B][2]*/, int B, int n,
+                                                          long long model_stride /*elements between models*/) {
+  constexpr int UNROLL = 4;
+  extern __shared__ uint32_t smem_u[];
+  uint32_t* keys = smem_u;       // n keys of this row
+  uint32_t* cand = smem_u + n;   // candidates that share the leading digit of the k-th largest key
   __shared__ uint32_t hist[256];
-  __shared__ uint32_t sh_prefix, sh_remaining, sh_ties_before;
+  __shared__ uint32_t sh_prefix, sh_remaining, sh_ncand, sh_ties_before, sh_neq;
+  __shared__ uint32_t warp_cnt[8];
   __shared__ float redf[16];
   const int model = blockIdx.y;
   const int row = blockIdx.x;
-  const long long base = ((long long)model * B + row) * n;
+  const long long base = (long long)model * model_stride + (long long)row * n;
+  const int n4 = n >> 2;
   int k = (int)sparsity[model];
   if (k > n) k = n;
-  for (int i = threadIdx.x; i < n; i += 256) keys[i] = f2key(scores[base + i]);
+
+  // ---- load the row once: keys to shared memory, per-thread maximum in a register
   if (threadIdx.x == 0) {
-    sh_prefix = 0;
-    sh_remaining = (uint32_t)k;
+    sh_ncand = 0;
+    sh_ties_before = 0;
   }
-  __syncthreads();
-  // find the key of the k-th largest element
-  for (int pass = 0; pass < 4; ++pass) {
-    const int shift = 24 - 8 * pass;
-    hist[threadIdx.x] = 0;
-    __syncthreads();
-    const uint32_t prefix = sh_prefix;
-    const uint32_t pmask = pass == 0 ? 0u : (0xFFFFFFFFu << (shift + 8));
-    for (int i = threadIdx.x; i < n; i += 256) {
-      const uint32_t kk = keys[i];
-      if ((kk & pmask) == prefix) atomicAdd(&hist[(kk >> shift) & 0xFF], 1u);
+  uint32_t my_max = 0;
+  const float4* src4 = reinterpret_cast<const float4*>(scores + base);
+  for (int i0 = 0; i0 < n4; i0 += 256 * UNROLL) {
+    float4 v[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const int i = i0 + u * 256 + threadIdx.x;
+      v[u] = i < n4 ? __ldg(src4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      uint32_t rem = sh_remaining;
-      int b = 255;
-      for (; b > 0; --b) {
-        if (hist[b] >= rem) break;
-        rem -= hist[b];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const int i = i0 + u * 256 + threadIdx.x;
+      if (i < n4) {
+        const uint4 kk = make_uint4(f2key(v[u].x), f2key(v[u].y), f2key(v[u].z), f2key(v[u].w));
+        reinterpret_cast<uint4*>(keys)[i] = kk;
+        my_max = max(max(my_max, kk.x), max(kk.y, max(kk.z, kk.w)));
       }
-      sh_prefix = prefix | (uint32_t(b) << shift);
-      sh_remaining = rem;  // how many elements equal (so far) to the prefix must still be taken
     }
-    __syncthreads();
   }
-  const uint32_t kth = sh_prefix;          // exact key of the k-th largest
-  const uint32_t take_ties = sh_remaining; // number of elements == kth to keep (lowest index first)
-  float l1 = 0.f, cnt = 0.f;
-  // elements equal to kth: keep the first `take_ties` in index order (serial scan over chunks)
-  if (threadIdx.x == 0) sh_ties_before = 0;
-  __syncthreads();
-  for (int i0 = 0; i0 < n; i0 += 256) {
-    const int i = i0 + threadIdx.x;
-    uint32_t kk = 0;
-    bool is_tie = false;
-    if (i < n) {
-      kk = keys[i];
-      is_tie = kk == kth;
-    }
-    // rank of this tie among ties of the chunk
-    const uint32_t ball = __ballot_sync(0xffffffffu, is_tie);
-    __shared__ uint32_t warp_cnt[8];
-    if ((threadIdx.x & 31) == 0) warp_cnt[threadIdx.x >> 5] = __popc(ball);
-    __syncthreads();
-    uint32_t before = sh_ties_before;
-    for (int w = 0; w < (threadIdx.x >> 5); ++w) before += warp_cnt[w];
-    before += __popc(ball & ((1u << (threadIdx.x & 31)) - 1u));
-    if (i < n) {
-      const bool keep = kk > kth || (is_tie && before < take_ties);
-      const float s = scores[base + i];
-      const float cv = (keep && s > 0.f) ? s : 0.f;
-      __nv_bfloat16 h, l;
-      split_bf16(cv, h, l);
-      c_hi[base + i] = h;
-      c_lo[base + i] = l;
-      l1 += cv;
-      cnt += cv > 0.f ? 1.f : 0.f;
-    }
-    __syncthreads();
+  // 4-pass 8-bit radix select of the `want`-th largest of a set of keys; `each(f)` calls f(key) for the keys this
+  // thread contributes. Leaves the key in sh_prefix, the number of elements equal to it still to take in
+  // sh_remaining and (last pass) their total count in sh_neq.
+  auto radix_select = [&](uint32_t want, auto&& each) {
     if (threadIdx.x == 0) {
-      uint32_t t = 0;
-      for (int w = 0; w < 8; ++w) t += warp_cnt[w];
-      sh_ties_before += t;
+      sh_prefix = 0;
+      sh_remaining = want;
     }
-    __syncthreads();
+    for (int pass = 0; pass < 4; ++pass) {
+      const int shift = 24 - 8 * pass;
+      hist[threadIdx.x] = 0;
+      __syncthreads();
+      const uint32_t prefix = sh_prefix;
+      const uint32_t pmask = pass == 0 ? 0u : (0xFFFFFFFFu << (shift + 8));
+      each([&](uint32_t kk, bool valid) { hist_add(hist, (kk >> shift) & 0xFF, valid && (kk & pmask) == prefix); });
+      __syncthreads();
+      pick_bin(hist, &sh_prefix, &sh_remaining, warp_cnt, shift, pass == 3 ? &sh_neq : nullptr);
+    }
+  };
+  // ---- a lower bound of the k-th largest key: the k-th largest of the 256 per-thread maxima (at least k elements
+  //      are >= it). Only elements >= that bound can be in the top k: typically one to a few k of them.
+  uint32_t bound = 0;                                     // k > 256: no pre-filter, every key is a candidate
+  if (k <= 256) {
+    radix_select((uint32_t)k, [&](auto&& f) { f(my_max, true); });
+    bound = sh_prefix;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n4; i += 256) {
+    const uint4 kk = reinterpret_cast<const uint4*>(keys)[i];
+    if (kk.x >= bound) cand[atomicAdd(&sh_ncand, 1u)] = kk.x;
+    if (kk.y >= bound) cand[atomicAdd(&sh_ncand, 1u)] = kk.y;
+    if (kk.z >= bound) cand[atomicAdd(&sh_ncand, 1u)] = kk.z;
+    if (kk.w >= bound) cand[atomicAdd(&sh_ncand, 1u)] = kk.w;
+  }
+  __syncthreads();
+  const int ncand = (int)sh_ncand;
+  // ---- exact selection among the candidates (order of `cand` is irrelevant)
+  radix_select((uint32_t)k, [&](auto&& f) {
+    for (int i0 = 0; i0 < ncand; i0 += 256) {
+      const int i = i0 + threadIdx.x;
+      f(i < ncand ? cand[i] : 0u, i < ncand);
+    }
+  });
+  const uint32_t kth = sh_prefix;          // exact key of the k-th largest
+  const uint32_t take_ties = sh_remaining; // number of elements == kth to keep
+  const bool all_ties_kept = sh_neq == take_ties;
+  float l1 = 0.f, cnt = 0.f;
+  uint2* out_hi = reinterpret_cast<uint2*>(c_hi + base);
+  uint2* out_lo = reinterpret_cast<uint2*>(c_lo + base);
+  auto emit = [&](int i, float c0, float c1, float c2, float c3) {
+    uint32_t h01, l01, h23, l23;
+    {
+      __nv_bfloat16 h[4], l[4];
+      split_bf16(c0, h[0], l[0]);
+      split_bf16(c1, h[1], l[1]);
+      split_bf16(c2, h[2], l[2]);
+      split_bf16(c3, h[3], l[3]);
+      h01 = pack_bf16(h[0], h[1]);
+      h23 = pack_bf16(h[2], h[3]);
+      l01 = pack_bf16(l[0], l[1]);
+      l23 = pack_bf16(l[2], l[3]);
+    }
+    out_hi[i] = make_uint2(h01, h23);
+    out_lo[i] = make_uint2(l01, l23);
+    l1 += c0 + c1 + c2 + c3;
+    cnt += (c0 > 0.f ? 1.f : 0.f) + (c1 > 0.f ? 1.f : 0.f) + (c2 > 0.f ? 1.f : 0.f) + (c3 > 0.f ? 1.f : 0.f);
+  };
+  if (all_ties_kept) {
+    // the common case (no exact tie straddling the cut): keep = key >= kth; values come back out of the keys
+    for (int i = threadIdx.x; i < n4; i += 256) {
+      const uint4 kk = reinterpret_cast<const uint4*>(keys)[i];
+      emit(i, kk.x >= kth ? key2relu(kk.x) : 0.f, kk.y >= kth ? key2relu(kk.y) : 0.f,
+           kk.z >= kth ? key2relu(kk.z) : 0.f, kk.w >= kth ? key2relu(kk.w) : 0.f);
+    }
+  } else {
+    // exact ties at the cut: keep the first `take_ties` of them in index order (ordered block scan)
+    for (int i0 = 0; i0 < n4; i0 += 256) {
+      const int i = i0 + threadIdx.x;
+      uint4 kk = make_uint4(0, 0, 0, 0);
+      if (i < n4) kk = reinterpret_cast<const uint4*>(keys)[i];
+      const uint32_t kv[4] = {kk.x, kk.y, kk.z, kk.w};
+      int mine = 0;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) mine += (i < n4 && kv[u] == kth) ? 1 : 0;
+      // exclusive prefix of tie counts over the block, in element order (thread t owns elements 4i..4i+3)
+      int incl = mine;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((threadIdx.x & 31) >= o) incl += v;
+      }
+      if ((threadIdx.x & 31) == 31) warp_cnt[threadIdx.x >> 5] = (uint32_t)incl;
+      __syncthreads();
+      uint32_t before = sh_ties_before + (uint32_t)(incl - mine);
+      for (int w = 0; w < (threadIdx.x >> 5); ++w) before += warp_cnt[w];
+      if (i < n4) {
+        float cv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const bool tie = kv[u] == kth;
+          const bool keep = kv[u] > kth || (tie && before < take_ties);
+          if (tie) ++before;
+          cv[u] = keep ? key2relu(kv[u]) : 0.f;
+        }
+        emit(i, cv[0], cv[1], cv[2], cv[3]);
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int w = 0; w < 8; ++w) t += warp_cnt[w];
+        sh_ties_before += t;
+      }
+      __syncthreads();
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {

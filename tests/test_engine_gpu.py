@@ -336,3 +336,33 @@ def test_fvu_and_l0_match_reference_after_training():
         assert abs(fvu_e - fvu_r) <= 0.01 * fvu_r + 1e-4, (i, fvu_e, fvu_r)
         assert abs(l0_e - l0_r) <= 0.01 * l0_r + 0.05, (i, l0_e, l0_r)
         assert fvu_r < 0.5                                      # it actually learned something
+
+
+def test_topk_exact_ties_break_by_lowest_index():
+    """Q8: torch.topk leaves ties unspecified; the engine keeps the lowest indices among keys equal to the k-th
+    score. Duplicated dictionary rows make every score appear exactly twice, so an odd k cuts through a tie."""
+    import sparse_coding_b200 as S
+    torch.manual_seed(0)
+    d, n, B, k = 32, 128, 64, 7
+    half = torch.randn(n // 2, d)
+    p = {"dict": torch.cat([half, half]).contiguous()}          # row j == row j + 64
+    b = {"sparsity": torch.tensor(k, dtype=torch.long)}
+    ens = S.FunctionalEnsemble([(p, b)], S.TopKEncoder, S.adam, {"lr": 1e-3}, device="cuda", no_stacking=True)
+    X = torch.randn(B, d).cuda()
+    loss, aux = ens.forward_batch(X)
+    c = aux["c"].dense()[0].cpu()
+    Wn = p["dict"] / p["dict"].norm(dim=-1, keepdim=True)
+    S64 = (X.cpu().double() @ Wn.double().T)
+    for r in range(B):
+        row = c[r]
+        assert torch.equal(row[:64] != 0, (row[:64] != 0))       # (shape sanity)
+        top = torch.topk(S64[r, :64], 4).values                  # distinct values: the 4 largest, each duplicated
+        assert bool((top > 0).all())
+        nz = (row != 0).nonzero().flatten().tolist()
+        assert len(nz) == k, (r, nz)
+        lo = [j for j in nz if j < 64]
+        hi = [j - 64 for j in nz if j >= 64]
+        assert len(lo) == 4 and len(hi) == 3                     # the tied pair at the cut keeps its lower index
+        assert set(hi) < set(lo)
+        cut = (set(lo) - set(hi)).pop()
+        assert abs(float(S64[r, cut]) - float(top[3])) < 1e-5    # ... and it is the 4th largest value
