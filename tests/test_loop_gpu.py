@@ -196,3 +196,45 @@ def test_on_device_evaluation_matches_learned_dict_metrics():
         assert abs(float(got["fvu"][i]) - float(O.fvu(held, ld.predict(held)))) <= 1e-4 * float(got["fvu"][i]) + 1e-6
         assert abs(float(got["mean_l0"][i]) - float((c != 0).float().sum(-1).mean())) <= 0.02
         assert abs(int(got["n_ever_active"][i]) - int((c != 0).any(0).sum())) <= 1
+
+
+def _child_steps(state_dict, batches, done):
+    """Body of a reference-style worker process (cluster_runs.py:15-36 `job_wrapper`): rebuild the ensemble from
+    its state_dict (device tensors arrive through CUDA IPC) and train on the parent's memory in place."""
+    import sparse_coding_b200 as S
+    torch.set_grad_enabled(False)
+    ens = S.FunctionalEnsemble.from_state(state_dict)
+    for x in batches:
+        ens.step_batch(x.to(ens.device))
+    torch.cuda.synchronize()
+    done.value = 1
+
+
+def test_spawned_worker_trains_parent_memory_in_place():
+    """The reference dispatches every chunk to a freshly spawned process per ensemble and relies on the child
+    mutating the parent's device tensors through CUDA IPC (cluster_runs.py:100-157, ensemble.py:125-161). The
+    engine-backed ensemble must survive that round trip: state_dict() pickles, from_state() in the child builds its
+    own plan/workspace, and parameters + Adam moments change in the parent."""
+    import torch.multiprocessing as mp
+    import sparse_coding_b200 as S
+    torch.manual_seed(0)
+    d, n, B = 64, 128, 256
+    models = [S.FunctionalTiedSAE.init(d, n, a) for a in (1e-3, 1e-2)]
+    ens = S.FunctionalEnsemble(_clone(models), S.FunctionalTiedSAE, S.adam, {"lr": 1e-3}, device="cuda:0")
+    twin = S.FunctionalEnsemble(_clone(models), S.FunctionalTiedSAE, S.adam, {"lr": 1e-3}, device="cuda:0")
+    gen = torch.Generator().manual_seed(1)
+    batches = [torch.randn(B, d, generator=gen) for _ in range(3)]
+    before = ens.params["encoder"].clone()
+    ens.to_shared_memory()
+    ctx = mp.get_context("spawn")
+    done = ctx.Value("i", 0)
+    proc = ctx.Process(target=_child_steps, args=(ens.state_dict(), batches, done))
+    proc.start()
+    proc.join(timeout=300)
+    assert proc.exitcode == 0 and done.value == 1
+    for x in batches:
+        twin.step_batch(x.cuda())
+    torch.cuda.synchronize()
+    assert not torch.equal(ens.params["encoder"], before)
+    assert torch.equal(ens.params["encoder"], twin.params["encoder"])
+    assert torch.equal(ens.optim_states["nu"]["encoder_bias"], twin.optim_states["nu"]["encoder_bias"])
