@@ -55,6 +55,7 @@ struct sce_plan {
   sce_desc d;
   sce_buffers b;
   int sms;
+  int device;  // CUDA device the plan was created on (the caller keeps it current for every call)
   int xm;  // number of distinct input batches (1 shared, or M)
   // workspace carve-up
   float* x_stage;                 // [xm, Bmax, d] staging for host-fed steps
@@ -279,10 +280,11 @@ static int launch_gemm_t(const sce_plan* p, const GemmMaps& maps, int nsets, con
                          const typename Epi::Params& epi, cudaStream_t st) {
   using SM = GemmSmem<BN, BK, A_MN, B_MN, STAGES, Epi::kWarpStageBytes, CTA2>;
   auto kern = gemm_split_kernel<Epi, BN, BK, A_MN, B_MN, STAGES, SPLIT_ACC, CTA2>;
-  static bool configured = false;
-  if (!configured) {
+  // the opt-in to > 48 KB of dynamic shared memory is per device: remember which devices have it
+  static bool configured[64] = {};
+  if (p->device < 0 || p->device >= 64 || !configured[p->device]) {
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kBytes));
-    configured = true;
+    if (p->device >= 0 && p->device < 64) configured[p->device] = true;
   }
   GemmParams<typename Epi::Params> gp;
   memset(&gp, 0, sizeof(gp));
@@ -434,10 +436,10 @@ static int run_pipeline(sce_plan* p, const float* x, int B, float* x_hat, bool b
     if (rc) return rc;
     ++launches;
     if ((size_t)n * 8 > 200 * 1024) return fail(SCE_ERR_INVALID, "top-k: n = %d exceeds the shared-memory row buffers", n);
-    static bool cfg = false;
-    if (!cfg) {
+    static bool cfg[64] = {};
+    if (p->device < 0 || p->device >= 64 || !cfg[p->device]) {
       CUDA_TRY(cudaFuncSetAttribute(topk_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      cfg = true;
+      if (p->device >= 0 && p->device < 64) cfg[p->device] = true;
     }
     // one block per (row, model); scores / codes of model m start at m * batch_max * n
     topk_select_kernel<<<dim3(B, M), 256, (size_t)n * 8, st>>>(reinterpret_cast<const float*>(p->dz_hi), p->b.sparsity,
@@ -570,6 +572,7 @@ int sce_plan_create(const sce_desc* desc, const sce_buffers* buffers, sce_plan**
   p->d = *desc;
   p->b = b;
   p->sms = sms;
+  p->device = dev;
   p->xm = desc->x_per_model ? desc->n_models : 1;
   // CTA pairs by default for all four GEMMs (same-box A/B in profiles/r01g_pair_tuning.txt: -10 % encode,
   // -9 % decode, -3 % dcode, -21 % weight gradient on that box; env SCE_TUNE_PAIR_* = 0 switches one back)

@@ -238,3 +238,20 @@ def test_spawned_worker_trains_parent_memory_in_place():
     assert not torch.equal(ens.params["encoder"], before)
     assert torch.equal(ens.params["encoder"], twin.params["encoder"])
     assert torch.equal(ens.optim_states["nu"]["encoder_bias"], twin.optim_states["nu"]["encoder_bias"])
+
+
+def test_two_devices_in_one_process():
+    """Plans on different GPUs of one process (the reference builds one ensemble per device in the parent,
+    big_sweep_experiments.py:265-291). Skipped on single-GPU boxes."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import sparse_coding_b200 as S
+    torch.manual_seed(0)
+    models = [S.FunctionalTiedSAE.init(64, 128, a) for a in (1e-3, 1e-2)]
+    X = torch.randn(256, 64)
+    outs = []
+    for dev in ("cuda:0", "cuda:1"):
+        ens = S.FunctionalEnsemble(_clone(models), S.FunctionalTiedSAE, S.adam, {"lr": 1e-3}, device=dev)
+        loss, _ = ens.step_batch(X.to(dev))
+        outs.append((loss["loss"].cpu(), ens.params["encoder"].cpu()))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
