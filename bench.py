@@ -355,6 +355,12 @@ def main():
                          "issued_tflops": alg_flops_dw * args.bwd_passes / (dw_ms * 1e-3) / 1e12 if dw_ms > 0 else None,
                          "step_alg_tflops": step_flops / (ms / K * 1e-3) / 1e12},
             "phases_ms": per_phase,
+            # every GEMM phase against the same peak: algorithmic (fp32-equivalent) and issued (x passes) TFLOP/s
+            "gemms": {ph: {"alg_tflops": units * 2.0 * M * B * n * d / (per_phase[ph] * 1e-3) / 1e12,
+                           "issued_tflops": units * 2.0 * M * B * n * d * passes / (per_phase[ph] * 1e-3) / 1e12,
+                           "frac_of_peak_issued": units * 2.0 * M * B * n * d * passes / (per_phase[ph] * 1e-3) / 1e12 / pk["bf16_tflops"]}
+                      for ph, units, passes in (("encode", 1, 3), ("decode", 1, 3), ("dcode", 1, args.bwd_passes),
+                                                ("dw", 2, args.bwd_passes)) if per_phase[ph] > 0},
             "final_loss_mean": float(final_loss.mean()),
         }
         tr = ncu_traffic()
