@@ -68,6 +68,7 @@ struct sce_plan {
   float *part_enc, *part_dec, *db_part, *bnorm, *l1_over_b, *loss_stage, *nnz_stage;
   int tiles_mB_max;
   std::map<int, BatchMaps*>* maps;
+  int split_decode;  // 1: separate TMEM accumulators for hi*hi and the cross terms in the decode GEMM (default)
   int pair_encode, pair_decode, pair_dcode, pair_dw;  // 1: run that GEMM on CTA pairs (cta_group::2, 256-row tiles)
   int bk_encode, bk_decode, bk_dcode;  // K block (64: 128-byte swizzle, 32: 64-byte swizzle) of the K-major GEMMs
   int last_launches;
@@ -464,8 +465,12 @@ static int run_pipeline(sce_plan* p, const float* x, int B, float* x_hat, bool b
   dp.tiles_m = tiles_mB;
   dp.gscale = 2.0f / ((float)B * (float)dd);
   dp.tiles_n = dd > 128 ? (dd + 255) / 256 : 1;
-  rc = launch_k<EpiDecode, true, true>(dd > 128, p->bk_decode, use_pair(p->pair_decode, B), p, maps->decode, 1, one, one, n,
-                                       d.fwd_passes, B, dd, dp, st);
+  if (p->split_decode)
+    rc = launch_k<EpiDecode, true, true>(dd > 128, p->bk_decode, use_pair(p->pair_decode, B), p, maps->decode, 1, one, one,
+                                         n, d.fwd_passes, B, dd, dp, st);
+  else
+    rc = launch_k<EpiDecode, true, false>(dd > 128, p->bk_decode, use_pair(p->pair_decode, B), p, maps->decode, 1, one, one,
+                                          n, d.fwd_passes, B, dd, dp, st);
   if (rc) return rc;
   ++launches;
 
@@ -580,6 +585,11 @@ int sce_plan_create(const sce_desc* desc, const sce_buffers* buffers, sce_plan**
   p->pair_decode = tune_flag("SCE_TUNE_PAIR_DECODE", 1);
   p->pair_dcode = tune_flag("SCE_TUNE_PAIR_DCODE", 1);
   p->pair_dw = tune_flag("SCE_TUNE_PAIR_DW", 1);
+  // The truncation bias of a single accumulation chain grows with the reduction length (about 3.7e-9 * n on x_hat,
+  // up to ~3.6x that on the loss): harmless at n <= 4096 (1.5e-5 / 3e-5 measured), over the 1e-4 bar near
+  // n = 16384-32768. Splitting costs the decode GEMM its accumulator double-buffering (1.14 -> 1.29 ms at config 2,
+  // profiles/r01i_split_decode_tuning.txt), so it is switched on where it is needed.
+  p->split_decode = tune_flag("SCE_TUNE_SPLIT_DECODE", desc->n > 4096 ? 1 : 0);
   p->bk_encode = tune_bk("SCE_TUNE_BK_ENCODE", 64);
   p->bk_decode = tune_bk("SCE_TUNE_BK_DECODE", 32);
   p->bk_dcode = tune_bk("SCE_TUNE_BK_DCODE", 64);
