@@ -300,17 +300,20 @@ def test_other_config_shapes(shape):
     assert bool((after["loss"] < before).all()) and all(torch.isfinite(v).all() for v in ens.params.values())
 
 
-def test_fvu_and_l0_match_reference_after_training():
+@pytest.mark.parametrize("bwd_passes", [3, 1])
+def test_fvu_and_l0_match_reference_after_training(bwd_passes):
     """The quality half of the metric ("FVU vs ref"): train engine and oracle from the same initial state on the
     same 300 batches, export LearnedDicts, compare FVU (standard_metrics.py:310-314) and mean L0 (:305-308) on
-    held-out data."""
+    held-out data. Also run with single-pass bf16 backward GEMMs (the optional fast mode): the trained dictionaries
+    must be just as good."""
     import sparse_coding_b200 as S
     from sparse_coding_b200.train_loop import unstacked_to_learned_dicts
     torch.manual_seed(0)
     d, n, B = 64, 256, 512
     models = [S.FunctionalTiedSAE.init(d, n, a) for a in (3e-4, 1e-3, 3e-3)]
     clone = lambda ms: [({k: v.clone() for k, v in p.items()}, {k: v.clone() for k, v in b.items()}) for p, b in ms]
-    ens = S.FunctionalEnsemble(clone(models), S.FunctionalTiedSAE, S.adam, {"lr": 1e-3}, device="cuda")
+    ens = S.FunctionalEnsemble(clone(models), S.FunctionalTiedSAE, S.adam, {"lr": 1e-3}, device="cuda",
+                               bwd_passes=bwd_passes)
     ref = O.RefPortEnsemble(clone(models), O.SIG_LOSSES["tied"], lr=1e-3)
     gen = torch.Generator().manual_seed(1)
     feats = torch.randn(384, d, generator=gen)

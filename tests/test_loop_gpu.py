@@ -255,3 +255,43 @@ def test_two_devices_in_one_process():
         loss, _ = ens.step_batch(X.to(dev))
         outs.append((loss["loss"].cpu(), ens.params["encoder"].cpu()))
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
+def test_c_abi_error_paths_on_device():
+    """Errors cross the ABI as negative status + thread-local message, never as a crash: wrong device class of
+    arguments, batch larger than the plan, misaligned / short workspace."""
+    import sparse_coding_b200 as S
+    from sparse_coding_b200 import _lib
+    lib = _lib.load()
+    torch.manual_seed(0)
+    models = [S.FunctionalTiedSAE.init(32, 64, 1e-3)]
+    ens = S.FunctionalEnsemble(models, S.FunctionalTiedSAE, S.adam, {"lr": 1e-3}, device="cuda")
+    ens.step_batch(torch.randn(128, 32).cuda())                       # plan for batch_max = 128
+    x = torch.randn(256, 32).cuda()
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    assert lib.sce_step(ens._plan, x.data_ptr(), 256, None, None, stream) == -1
+    assert b"batch_max" in lib.sce_last_error()
+    assert lib.sce_step(ens._plan, None, 64, None, None, stream) == -1
+    assert lib.sce_read_code(ens._plan, 0, x.data_ptr(), stream) == -1
+    # the Python layer re-plans transparently for a larger batch
+    loss, _ = ens.step_batch(x)
+    assert torch.isfinite(loss["loss"]).all()
+    # short / misaligned workspace
+    desc = _lib.SceDesc(variant=0, n_models=1, d=32, n=64, batch_max=128, x_per_model=0, lr=1e-3, beta1=0.9, beta2=0.999,
+                        eps=1e-8, eps_root=0.0, adam_count_mode=0, fwd_passes=3, bwd_passes=3, norm_floor=1e-8)
+    need = lib.sce_workspace_bytes(C.byref(desc))
+    ws = torch.empty(need + 2048, dtype=torch.uint8, device="cuda")
+    p = ens.params
+    mu, nu = ens.optim_states["mu"], ens.optim_states["nu"]
+    bufs = _lib.SceBuffers(encoder=p["encoder"].data_ptr(), encoder_bias=p["encoder_bias"].data_ptr(),
+                           encoder_m=mu["encoder"].data_ptr(), encoder_v=nu["encoder"].data_ptr(),
+                           bias_m=mu["encoder_bias"].data_ptr(), bias_v=nu["encoder_bias"].data_ptr(),
+                           workspace=(ws.data_ptr() + 1023) // 1024 * 1024 + 16, workspace_bytes=need)
+    plan = C.c_void_p()
+    assert lib.sce_plan_create(C.byref(desc), C.byref(bufs), C.byref(plan)) == -3 and b"aligned" in lib.sce_last_error()
+    bufs.workspace = (ws.data_ptr() + 1023) // 1024 * 1024
+    bufs.workspace_bytes = need - 1
+    assert lib.sce_plan_create(C.byref(desc), C.byref(bufs), C.byref(plan)) == -3 and b"too small" in lib.sce_last_error()
+    bufs.workspace_bytes = need
+    assert lib.sce_plan_create(C.byref(desc), C.byref(bufs), C.byref(plan)) == 0
+    assert lib.sce_plan_destroy(plan) == 0
