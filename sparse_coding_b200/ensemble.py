@@ -379,6 +379,16 @@ class FunctionalEnsemble:
                                                  self._out_nnz.data_ptr(), self._stream()), "sce_grads")
             return g, (self._losses_dict(), self._aux(B))
 
+    def calc_grads(self, params, buffers, minibatches):
+        """Reference-shaped entry point (``self.calc_grads`` of ensemble.py:99-123): gradients of ``sig.loss`` for
+        the stacked models on ``minibatches`` [M, B, d]. ``params`` / ``buffers`` must be this ensemble's own trees
+        (the engine reads the tensors it was planned on). Returns ``(grads, (loss_data, aux))``."""
+        if params is not self.params or buffers is not self.buffers:
+            raise ValueError("calc_grads operates on the ensemble's own params/buffers (in-place engine)")
+        if minibatches.dim() == 3 and minibatches.stride(0) == 0:      # an expand()-ed shared batch: don't copy it M times
+            return self.grads_batch(minibatches[0], expand_dims=True)
+        return self.grads_batch(minibatches, expand_dims=False)
+
     def refresh(self):
         """Call after modifying ``params`` / ``buffers`` from outside the engine (re-derives the bf16 operand
         copies and the cached centring check)."""

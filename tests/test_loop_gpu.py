@@ -154,6 +154,21 @@ def test_per_model_batches_expand_dims_false():
         assert relnorm(grads["encoder"][i], f["grads"]["encoder"]) <= 2e-4
 
 
+def test_calc_grads_reference_shape():
+    """ensemble.calc_grads(params, buffers, batch.expand(M, B, d)) as step_batch drives it in the reference
+    (ensemble.py:177-180)."""
+    import sparse_coding_b200 as S
+    torch.manual_seed(0)
+    models = [S.FunctionalTiedSAE.init(32, 64, a) for a in (1e-3, 1e-2)]
+    ens = S.FunctionalEnsemble(_clone(models), S.FunctionalTiedSAE, S.adam, {"lr": 1e-3}, device="cuda")
+    X = torch.randn(48, 32).cuda()
+    g1, (l1, _) = ens.calc_grads(ens.params, ens.buffers, X.expand(2, 48, 32))
+    g2, (l2, _) = ens.grads_batch(X)
+    assert torch.equal(g1["encoder"], g2["encoder"]) and torch.equal(l1["loss"], l2["loss"])
+    with pytest.raises(ValueError):
+        ens.calc_grads({k: v.clone() for k, v in ens.params.items()}, ens.buffers, X.expand(2, 48, 32))
+
+
 def test_host_fed_step_through_c_abi():
     """sce_step_host: HOST batch in, HOST losses out (the e2e path of bench.py), identical to the device path."""
     import sparse_coding_b200 as S
