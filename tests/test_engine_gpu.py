@@ -369,3 +369,73 @@ def test_topk_exact_ties_break_by_lowest_index():
         assert set(hi) < set(lo)
         cut = (set(lo) - set(hi)).pop()
         assert abs(float(S64[r, cut]) - float(top[3])) < 1e-5    # ... and it is the 4th largest value
+
+
+def test_random_shape_sweep():
+    """Seeded sweep over odd shapes (every multiple-of-8 corner the plan accepts: tiny d / n, n < one tile, B = 1,
+    B straddling 128/256-row tiles, single model, many models) for tied / untied / masked / top-k against the fp64
+    oracle: loss within 1e-4, x̂ within 1e-4, gradients within 5e-4 with the ReLU kink pinned to the engine's side."""
+    import random
+    import sparse_coding_b200 as S
+    rng = random.Random(1234)
+    kinds = ["tied", "untied", "masked_tied", "topk"]
+    cases = [(1, 8, 8, 1), (2, 8, 16, 5), (1, 16, 8, 130), (3, 24, 40, 257), (2, 136, 264, 129), (1, 8, 520, 64),
+             (2, 264, 24, 300)]
+    for _ in range(14):
+        cases.append((rng.choice([1, 2, 3, 5]), 8 * rng.randint(1, 40), 8 * rng.randint(1, 70), rng.randint(1, 400)))
+    for ci, (M, d, n, B) in enumerate(cases):
+        kind = kinds[ci % len(kinds)]
+        torch.manual_seed(ci)
+        gen = torch.Generator().manual_seed(1000 + ci)
+        if kind == "tied":
+            models = [S.FunctionalTiedSAE.init(d, n, 10 ** rng.uniform(-4, -2)) for _ in range(M)]
+            sig = S.FunctionalTiedSAE
+        elif kind == "untied":
+            models = [S.FunctionalSAE.init(d, n, 10 ** rng.uniform(-4, -2), bias_decay=rng.choice([0.0, 0.05])) for _ in range(M)]
+            sig = S.FunctionalSAE
+        elif kind == "masked_tied":
+            models = [S.FunctionalMaskedTiedSAE.init(d, 8 * rng.randint(1, n // 8), n, 10 ** rng.uniform(-4, -2)) for _ in range(M)]
+            sig = S.FunctionalMaskedTiedSAE
+        else:
+            models = [S.TopKEncoder.init(d, n, rng.randint(1, min(n, 24))) for _ in range(M)]
+            sig = S.TopKEncoder
+        for p, _b in models:
+            if "encoder_bias" in p:
+                p["encoder_bias"] = 0.05 * torch.randn(n, generator=gen)
+        ens = S.FunctionalEnsemble([({k: v.clone() for k, v in p.items()}, b) for p, b in models], sig, S.adam,
+                                   {"lr": 1e-3}, device="cuda", no_stacking=(kind == "topk"))
+        X = torch.randn(B, d, generator=gen)
+        grads, (loss, aux) = ens.grads_batch(X.cuda())
+        code = aux["c"].dense().cpu()                      # before the next engine call reuses the code buffers
+        _, _, x_hat = ens.forward_batch(X.cuda(), return_x_hat=True)
+        tag = (ci, kind, M, d, n, B)
+        for i, (p, b) in enumerate(models):
+            pd = {k: v.double() for k, v in p.items()}
+            Xd = X.double()
+            if kind == "topk":
+                k = int(b["sparsity"])
+                Wn, _ = O.unit_rows(pd["dict"], floor=None)
+                Sc = Xd @ Wn.T
+                support = code[i] > 0
+                kept = torch.where(support, Sc, torch.full_like(Sc, float("inf"))).min(-1).values
+                dropped = torch.where(support, torch.full_like(Sc, -float("inf")), Sc).max(-1).values
+                assert int(support.sum(-1).max()) <= k and bool((kept >= dropped.clamp(min=0) - 1e-5).all()), tag
+                xh = (Sc.clamp(min=0) * support) @ Wn
+                ref_loss = (Xd - xh).pow(2).mean()
+                assert relnorm(x_hat[i], xh) <= REL, tag
+                assert abs(float(loss["loss"][i]) - float(ref_loss)) <= REL * float(ref_loss), tag
+                continue
+            mask = b["coef_mask"] if kind == "masked_tied" else None
+            alpha = float(b["l1_alpha"])
+            if kind == "untied":
+                f0 = O.untied_forward(pd["encoder"], pd["encoder_bias"], pd["decoder"], Xd, alpha, float(b["bias_decay"]))
+            else:
+                f0 = O.tied_forward(pd["encoder"], pd["encoder_bias"], Xd, alpha, 0.0, mask)
+            assert relnorm(x_hat[i], f0["x_hat"]) <= REL, tag
+            assert abs(float(loss["loss"][i]) - float(f0["loss"])) <= REL * abs(float(f0["loss"])) + 1e-12, tag
+            if kind != "untied":
+                active = torch.where(f0["Z"].abs() < 1e-5, code[i] > 0, f0["Z"] > 0)
+                f = O.tied_grads(pd["encoder"], pd["encoder_bias"], Xd, alpha, 0.0, mask, active=active)
+                assert relnorm(grads["encoder"][i], f["grads"]["encoder"]) <= 5e-4, tag
+                assert relnorm(grads["encoder_bias"][i], f["grads"]["encoder_bias"]) <= 5e-4, tag
+        del ens
