@@ -49,6 +49,9 @@ struct GemmMaps {  // tensor maps of one GEMM for one batch size
 struct BatchMaps {
   GemmMaps encode, decode, dcode, dw_enc, dw_dec;
   CUtensorMap st_c_hi, st_c_lo, st_dz_hi, st_dz_lo;  // epilogue TMA-store maps
+  cudaGraphExec_t graph;       // captured step for this batch size (launch-bound shapes), or nullptr
+  float *graph_losses, *graph_nnz;
+  int graph_launches, eager_steps;
 };
 
 struct sce_plan {
@@ -68,6 +71,8 @@ struct sce_plan {
   float *part_enc, *part_dec, *db_part, *bnorm, *l1_over_b, *loss_stage, *nnz_stage;
   int tiles_mB_max;
   std::map<int, BatchMaps*>* maps;
+  cudaStream_t cap_stream;  // private stream the step is captured on
+  int use_graph;     // 1: replay the step as a CUDA graph (launch-bound shapes; env SCE_GRAPH overrides)
   int split_decode;  // 1: separate TMEM accumulators for hi*hi and the cross terms in the decode GEMM (default)
   int pair_encode, pair_decode, pair_dcode, pair_dw;  // 1: run that GEMM on CTA pairs (cta_group::2, 256-row tiles)
   int bk_encode, bk_decode, bk_dcode;  // K block (64: 128-byte swizzle, 32: 64-byte swizzle) of the K-major GEMMs
@@ -590,6 +595,11 @@ int sce_plan_create(const sce_desc* desc, const sce_buffers* buffers, sce_plan**
   // n = 16384-32768. Splitting costs the decode GEMM its accumulator double-buffering (1.14 -> 1.29 ms at config 2,
   // profiles/r01i_split_decode_tuning.txt), so it is switched on where it is needed.
   p->split_decode = tune_flag("SCE_TUNE_SPLIT_DECODE", desc->n > 4096 ? 1 : 0);
+  {
+    // ~30 M B n d tensor FLOPs are issued per step; below ~3e11 (a fifth of a millisecond) launches dominate
+    const double issued = 30.0 * desc->n_models * (double)desc->batch_max * desc->n * desc->d;
+    p->use_graph = tune_flag("SCE_GRAPH", issued < 3e11 ? 1 : 0);
+  }
   p->bk_encode = tune_bk("SCE_TUNE_BK_ENCODE", 64);
   p->bk_decode = tune_bk("SCE_TUNE_BK_DECODE", 32);
   p->bk_dcode = tune_bk("SCE_TUNE_BK_DCODE", 64);
@@ -601,8 +611,12 @@ int sce_plan_create(const sce_desc* desc, const sce_buffers* buffers, sce_plan**
 
 int sce_plan_destroy(sce_plan* plan) {
   if (!plan) return SCE_OK;
-  for (auto& kv : *plan->maps) delete kv.second;
+  for (auto& kv : *plan->maps) {
+    if (kv.second->graph) cudaGraphExecDestroy(kv.second->graph);
+    delete kv.second;
+  }
   delete plan->maps;
+  if (plan->cap_stream) cudaStreamDestroy(plan->cap_stream);
   if (plan->prof_ev) {
     for (int i = 0; i < kProfMaxSteps * (SCE_PHASE_COUNT + 1); ++i) cudaEventDestroy(plan->prof_ev[i]);
     free(plan->prof_ev);
@@ -636,15 +650,14 @@ int sce_forward(sce_plan* p, const float* x, int B, float* x_hat, float* out_los
   return run_pipeline(p, x, B, x_hat, false, out_losses, out_nnz, static_cast<cudaStream_t>(stream));
 }
 
-int sce_step(sce_plan* p, const float* x, int B, float* out_losses, float* out_nnz, void* stream) {
-  if (!p) return fail(SCE_ERR_INVALID, "plan is NULL");
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
+// every launch of one optimisation step, in order, on `st` (also what gets captured into a CUDA graph)
+static int step_launches(sce_plan* p, const float* x, int B, float* out_losses, float* out_nnz, long long t,
+                         cudaStream_t st) {
   int rc = run_pipeline(p, x, B, nullptr, true, out_losses, out_nnz, st);
   if (rc) return rc;
   const sce_desc& d = p->d;
   const long long rows = (long long)d.n_models * d.n;
-  p->step += 1;
-  const AdamHyper h = hyper_for(p, p->step);
+  const AdamHyper h = hyper_for(p, t);
   int launches = p->last_launches;
   if (d.variant == SCE_UNTIED) {
     rc = launch_dict_rows<MODE_ADAM>(p->b.encoder, p->dw_enc, p->b.encoder_m, p->b.encoder_v, p->wenc_hi, p->wenc_lo,
@@ -670,8 +683,74 @@ int sce_step(sce_plan* p, const float* x, int B, float* out_losses, float* out_n
     ++launches;
   }
   prof_mark(p, SCE_PHASE_COUNT, st);
-  if (p->prof_on && p->prof_steps < kProfMaxSteps) p->prof_steps += 1;
   p->last_launches = launches;
+  return SCE_OK;
+}
+
+// Launch-bound shapes (a step of ~10 kernels that each run a few microseconds, e.g. BASELINE config 1) replay the
+// step as one CUDA graph: the batch is first copied into the plan's staging buffer so that every kernel argument is
+// stable, the graph is captured on the second step at a given batch size (the first one runs eagerly and performs
+// the one-off cudaFuncSetAttribute calls) and re-captured if the caller's output pointers change.
+static bool graph_eligible(const sce_plan* p) {
+  if (p->prof_on) return false;                                   // per-phase events are recorded eagerly
+  if (p->d.adam_count_mode != SCE_ADAM_FROZEN_T1) return false;   // bias correction is a kernel argument that moves
+  return p->use_graph != 0;
+}
+
+int sce_step(sce_plan* p, const float* x, int B, float* out_losses, float* out_nnz, void* stream) {
+  if (!p) return fail(SCE_ERR_INVALID, "plan is NULL");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (B < 1 || B > p->d.batch_max) return fail(SCE_ERR_INVALID, "B = %d outside [1, batch_max = %d]", B, p->d.batch_max);
+  if (!x) return fail(SCE_ERR_INVALID, "x is NULL");
+  int rc;
+  if (!graph_eligible(p)) {
+    rc = step_launches(p, x, B, out_losses, out_nnz, p->step + 1, st);
+  } else {
+    BatchMaps* maps = nullptr;
+    rc = build_maps(p, B, &maps);
+    if (rc) return rc;
+    const size_t bytes = (size_t)p->xm * B * p->d.d * sizeof(float);
+    if (x != p->x_stage) CUDA_TRY(cudaMemcpyAsync(p->x_stage, x, bytes, cudaMemcpyDeviceToDevice, st));
+    if (maps->graph && (maps->graph_losses != out_losses || maps->graph_nnz != out_nnz)) {
+      cudaGraphExecDestroy(maps->graph);
+      maps->graph = nullptr;
+      maps->eager_steps = 1;
+    }
+    if (maps->graph) {
+      CUDA_TRY(cudaGraphLaunch(maps->graph, st));
+      p->last_launches = maps->graph_launches;
+      rc = SCE_OK;
+    } else if (maps->eager_steps == 0) {
+      maps->eager_steps = 1;
+      rc = step_launches(p, p->x_stage, B, out_losses, out_nnz, 1, st);
+    } else {
+      // capture on a private stream (the caller's may be the legacy default stream, which cannot be captured);
+      // capturing records the launches without running them, the instantiated graph is launched on `st`
+      cudaGraph_t g = nullptr;
+      if (!p->cap_stream) CUDA_TRY(cudaStreamCreateWithFlags(&p->cap_stream, cudaStreamNonBlocking));
+      CUDA_TRY(cudaStreamBeginCapture(p->cap_stream, cudaStreamCaptureModeThreadLocal));
+      rc = step_launches(p, p->x_stage, B, out_losses, out_nnz, 1, p->cap_stream);
+      cudaError_t ce = cudaStreamEndCapture(p->cap_stream, &g);
+      if (rc == SCE_OK && ce == cudaSuccess && g) {
+        cudaGraphExec_t ge = nullptr;
+        ce = cudaGraphInstantiate(&ge, g, 0);
+        cudaGraphDestroy(g);
+        if (ce != cudaSuccess) return fail(SCE_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ce));
+        maps->graph = ge;
+        maps->graph_losses = out_losses;
+        maps->graph_nnz = out_nnz;
+        maps->graph_launches = p->last_launches;
+        CUDA_TRY(cudaGraphLaunch(maps->graph, st));
+      } else {
+        if (g) cudaGraphDestroy(g);
+        cudaGetLastError();
+        if (rc == SCE_OK) return fail(SCE_ERR_CUDA, "stream capture of the step failed: %s", cudaGetErrorString(ce));
+      }
+    }
+  }
+  if (rc) return rc;
+  p->step += 1;
+  if (p->prof_on && p->prof_steps < kProfMaxSteps) p->prof_steps += 1;
   return SCE_OK;
 }
 
