@@ -14,6 +14,15 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with `-m gpu`)")
 
 
+def pytest_sessionstart(session):
+    """The engine library is a build artefact (git-ignored). If a checkout has not been built yet, build it once
+    (nvcc cross-compiles sm_100a without a GPU) so that the ABI tests exercise the real thing."""
+    import subprocess
+    lib = os.path.join(ROOT, "sparse_coding_b200", "libsce.so")
+    if not os.path.exists(lib):
+        subprocess.run(["make", "-C", ROOT, "all"], check=True, stdout=subprocess.DEVNULL)
+
+
 @pytest.fixture(scope="session")
 def golden():
     import torch
