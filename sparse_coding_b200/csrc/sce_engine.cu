@@ -441,15 +441,16 @@ static int run_pipeline(sce_plan* p, const float* x, int B, float* x_hat, bool b
                                              one, dd, d.fwd_passes, B, n, sp, st);
     if (rc) return rc;
     ++launches;
-    if ((size_t)n * 8 > 200 * 1024) return fail(SCE_ERR_INVALID, "top-k: n = %d exceeds the shared-memory row buffers", n);
+    if ((size_t)n * 4 > 200 * 1024) return fail(SCE_ERR_INVALID, "top-k: n = %d exceeds the shared-memory row buffer", n);
+    const int use_cand = (size_t)n * 8 <= 200 * 1024;   // keys + candidate list, else keys only
     static bool cfg[64] = {};
     if (p->device < 0 || p->device >= 64 || !cfg[p->device]) {
       CUDA_TRY(cudaFuncSetAttribute(topk_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       if (p->device >= 0 && p->device < 64) cfg[p->device] = true;
     }
     // one block per (row, model); scores / codes of model m start at m * batch_max * n
-    topk_select_kernel<<<dim3(B, M), 256, (size_t)n * 8, st>>>(reinterpret_cast<const float*>(p->dz_hi), p->b.sparsity,
-                                                               p->c_hi, p->c_lo, p->part_enc, B, n, Bm * n);
+    topk_select_kernel<<<dim3(B, M), 256, (size_t)n * (use_cand ? 8 : 4), st>>>(
+        reinterpret_cast<const float*>(p->dz_hi), p->b.sparsity, p->c_hi, p->c_lo, p->part_enc, B, n, Bm * n, use_cand);
     ++launches;
     CUDA_TRY(cudaGetLastError());
     n_enc_parts = B;

@@ -386,7 +386,8 @@ __global__ void __launch_bounds__(256) topk_select_kernel(const float* __restric
                                                           __nv_bfloat16* __restrict__ c_hi,
                                                           __nv_bfloat16* __restrict__ c_lo,
                                                           float* __restrict__ part /*[M][B][2]*/, int B, int n,
-                                                          long long model_stride /*elements between models*/) {
+                                                          long long model_stride /*elements between models*/,
+                                                          int use_cand /*0: rows too long for a candidate list in smem*/) {
   constexpr int UNROLL = 4;
   extern __shared__ uint32_t smem_u[];
   uint32_t* keys = smem_u;       // n keys of this row
@@ -453,22 +454,33 @@ __global__ void __launch_bounds__(256) topk_select_kernel(const float* __restric
     bound = sh_prefix;
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < n4; i += 256) {
-    const uint4 kk = reinterpret_cast<const uint4*>(keys)[i];
-    if (kk.x >= bound) cand[atomicAdd(&sh_ncand, 1u)] = kk.x;
-    if (kk.y >= bound) cand[atomicAdd(&sh_ncand, 1u)] = kk.y;
-    if (kk.z >= bound) cand[atomicAdd(&sh_ncand, 1u)] = kk.z;
-    if (kk.w >= bound) cand[atomicAdd(&sh_ncand, 1u)] = kk.w;
-  }
-  __syncthreads();
-  const int ncand = (int)sh_ncand;
-  // ---- exact selection among the candidates (order of `cand` is irrelevant)
-  radix_select((uint32_t)k, [&](auto&& f) {
-    for (int i0 = 0; i0 < ncand; i0 += 256) {
-      const int i = i0 + threadIdx.x;
-      f(i < ncand ? cand[i] : 0u, i < ncand);
+  if (use_cand) {
+    for (int i = threadIdx.x; i < n4; i += 256) {
+      const uint4 kk = reinterpret_cast<const uint4*>(keys)[i];
+      if (kk.x >= bound) cand[atomicAdd(&sh_ncand, 1u)] = kk.x;
+      if (kk.y >= bound) cand[atomicAdd(&sh_ncand, 1u)] = kk.y;
+      if (kk.z >= bound) cand[atomicAdd(&sh_ncand, 1u)] = kk.z;
+      if (kk.w >= bound) cand[atomicAdd(&sh_ncand, 1u)] = kk.w;
     }
-  });
+    __syncthreads();
+    const int ncand = (int)sh_ncand;
+    // ---- exact selection among the candidates (order of `cand` is irrelevant)
+    radix_select((uint32_t)k, [&](auto&& f) {
+      for (int i0 = 0; i0 < ncand; i0 += 256) {
+        const int i = i0 + threadIdx.x;
+        f(i < ncand ? cand[i] : 0u, i < ncand);
+      }
+    });
+  } else {
+    // very long rows: no room for a candidate list, select over the keys that pass the bound in place
+    radix_select((uint32_t)k, [&](auto&& f) {
+      for (int i0 = 0; i0 < n; i0 += 256) {
+        const int i = i0 + threadIdx.x;
+        const uint32_t kk = i < n ? keys[i] : 0u;
+        f(kk, i < n && kk >= bound);
+      }
+    });
+  }
   const uint32_t kth = sh_prefix;          // exact key of the k-th largest
   const uint32_t take_ties = sh_remaining; // number of elements == kth to keep
   const bool all_ties_kept = sh_neq == take_ties;
