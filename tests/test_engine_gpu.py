@@ -440,3 +440,31 @@ def test_random_shape_sweep():
                 assert relnorm(grads["encoder"][i], f["grads"]["encoder"]) <= 5e-4, tag
                 assert relnorm(grads["encoder_bias"][i], f["grads"]["encoder_bias"]) <= 5e-4, tag
         del ens
+
+
+@pytest.mark.parametrize("kind", ["tied", "untied", "topk"])
+def test_bitwise_determinism(kind):
+    """Two runs from the same state on the same batches give bit-identical parameters, moments and losses: every
+    reduction in the engine has a fixed order (per-warp partials reduced by a finalisation kernel, no floating-point
+    atomics), unlike the reference's cuBLAS / atomics-based PyTorch path."""
+    import sparse_coding_b200 as S
+    d, n, B = 96, 320, 300
+    torch.manual_seed(0)
+    if kind == "tied":
+        models, sig = [S.FunctionalTiedSAE.init(d, n, a) for a in (1e-3, 1e-2)], S.FunctionalTiedSAE
+    elif kind == "untied":
+        models, sig = [S.FunctionalSAE.init(d, n, a, bias_decay=0.01) for a in (1e-3, 1e-2)], S.FunctionalSAE
+    else:
+        models, sig = [S.TopKEncoder.init(d, n, k) for k in (8, 24)], S.TopKEncoder
+    gen = torch.Generator().manual_seed(1)
+    batches = [torch.randn(B, d, generator=gen).cuda() for _ in range(6)]
+    clone = lambda ms: [({k: v.clone() for k, v in p.items()}, {k: v.clone() for k, v in b.items()}) for p, b in ms]
+    runs = []
+    for _ in range(2):
+        ens = S.FunctionalEnsemble(clone(models), sig, S.adam, {"lr": 1e-3}, device="cuda")
+        losses = [ens.step_batch(x)[0]["loss"].clone() for x in batches]
+        runs.append((ens.params, ens.optim_states, losses))
+    for k in runs[0][0]:
+        assert torch.equal(runs[0][0][k], runs[1][0][k])
+        assert torch.equal(runs[0][1]["nu"][k], runs[1][1]["nu"][k])
+    assert all(torch.equal(a, b) for a, b in zip(runs[0][2], runs[1][2]))
