@@ -72,6 +72,7 @@ struct sce_plan {
   int tiles_mB_max;
   std::map<int, BatchMaps*>* maps;
   cudaStream_t cap_stream;  // private stream the step is captured on
+  int dcode_passes, dw_passes;  // tensor passes of the two backward GEMMs (default: desc.bwd_passes)
   int use_graph;     // 1: replay the step as a CUDA graph (launch-bound shapes; env SCE_GRAPH overrides)
   int split_decode;  // 1: separate TMEM accumulators for hi*hi and the cross terms in the decode GEMM (default)
   int pair_encode, pair_decode, pair_dcode, pair_dw;  // 1: run that GEMM on CTA pairs (cta_group::2, 256-row tiles)
@@ -504,7 +505,7 @@ static int run_pipeline(sce_plan* p, const float* x, int B, float* x_hat, bool b
     zp.ldc = n;
     zp.tiles_m = tiles_mB;
     rc = launch_k<EpiDcode, false, false>(n > 128, p->bk_dcode, use_pair(p->pair_dcode, B), p, maps->dcode, 1, one, one, dd,
-                                          d.bwd_passes, B, n, zp, st);
+                                          p->dcode_passes, B, n, zp, st);
     if (rc) return rc;
     ++launches;
 
@@ -517,10 +518,10 @@ static int run_pipeline(sce_plan* p, const float* x, int B, float* x_hat, bool b
       sp.ld = dd;
       const bool pair = use_pair(p->pair_dw, n);
       if (dd > 128)
-        return pair ? launch_gemm_t<EpiStoreF32, 256, kBkDw, true, true, 6, true, true>(p, gm, nsets, ab, bb, B, d.bwd_passes, n, dd, sp, st)
-                    : launch_gemm_t<EpiStoreF32, 256, kBkDw, true, true, 4, true, false>(p, gm, nsets, ab, bb, B, d.bwd_passes, n, dd, sp, st);
-      return pair ? launch_gemm_t<EpiStoreF32, 128, kBkDw, true, true, 8, true, true>(p, gm, nsets, ab, bb, B, d.bwd_passes, n, dd, sp, st)
-                  : launch_gemm_t<EpiStoreF32, 128, kBkDw, true, true, 6, true, false>(p, gm, nsets, ab, bb, B, d.bwd_passes, n, dd, sp, st);
+        return pair ? launch_gemm_t<EpiStoreF32, 256, kBkDw, true, true, 6, true, true>(p, gm, nsets, ab, bb, B, p->dw_passes, n, dd, sp, st)
+                    : launch_gemm_t<EpiStoreF32, 256, kBkDw, true, true, 4, true, false>(p, gm, nsets, ab, bb, B, p->dw_passes, n, dd, sp, st);
+      return pair ? launch_gemm_t<EpiStoreF32, 128, kBkDw, true, true, 8, true, true>(p, gm, nsets, ab, bb, B, p->dw_passes, n, dd, sp, st)
+                  : launch_gemm_t<EpiStoreF32, 128, kBkDw, true, true, 6, true, false>(p, gm, nsets, ab, bb, B, p->dw_passes, n, dd, sp, st);
     };
     if (d.variant == SCE_UNTIED) {
       rc = dw(maps->dw_enc, 1, one, xb, p->dw_enc);
@@ -596,6 +597,10 @@ int sce_plan_create(const sce_desc* desc, const sce_buffers* buffers, sce_plan**
   // n = 16384-32768. Splitting costs the decode GEMM its accumulator double-buffering (1.14 -> 1.29 ms at config 2,
   // profiles/r01i_split_decode_tuning.txt), so it is switched on where it is needed.
   p->split_decode = tune_flag("SCE_TUNE_SPLIT_DECODE", desc->n > 4096 ? 1 : 0);
+  p->dcode_passes = desc->bwd_passes;
+  p->dw_passes = desc->bwd_passes;
+  if (const char* v = getenv("SCE_TUNE_DCODE_PASSES")) p->dcode_passes = atoi(v) == 1 ? 1 : 3;
+  if (const char* v = getenv("SCE_TUNE_DW_PASSES")) p->dw_passes = atoi(v) == 1 ? 1 : 3;
   {
     // ~30 M B n d tensor FLOPs are issued per step; below ~3e11 (a fifth of a millisecond) launches dominate
     const double issued = 30.0 * desc->n_models * (double)desc->batch_max * desc->n * desc->d;
