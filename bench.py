@@ -125,6 +125,21 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+class _StdoutGuard:
+    """stdout must carry exactly ONE JSON line. Libraries (NCCL's version banner, for one) write to file descriptor
+    1 behind Python's back, so fd 1 is pointed at stderr for the whole run and the JSON goes to a saved duplicate of
+    the real stdout."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self.real = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, obj):
+        sys.stdout.flush()
+        os.write(self.real, (json.dumps(obj) + "\n").encode())
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -184,7 +199,7 @@ def cpu_reference_rate(M, d, n, B_full, budget_s=20.0, steps=1, warmup=1):
     return Bs / dt, f"{steps} step(s) of the full {M}-model ensemble at batch {Bs} of {B_full} rows (fp32, torch CPU)", cores, dt
 
 
-def run_reference(args, rank, world):
+def run_reference(args, rank, world, out):
     if rank != 0:
         return
     M, d, n, B, desc = WORKLOADS[args.workload]
@@ -198,7 +213,7 @@ def run_reference(args, rank, world):
         "cpu_baseline": {"value": rate, "unit": "activations/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": rate, "unit": "activations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    out.emit(line)
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -219,8 +234,9 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
+    out = _StdoutGuard()
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, rank, world, out)
         return
 
     import torch.distributed as dist
@@ -376,7 +392,7 @@ def main():
             rate, sample, cores, _ = cpu_reference_rate(M, d, n, B, budget_s=20.0)
             line["cpu_baseline"] = {"value": rate, "unit": "activations/s", "cores": cores, "kind": "port",
                                     "sample": sample}
-        print(json.dumps(line))
+        out.emit(line)
     if world > 1:
         dist.destroy_process_group()
 
