@@ -227,7 +227,10 @@ def main():
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--bwd-passes", type=int, default=3, choices=[1, 3])
+    ap.add_argument("--arith", default="auto", choices=["auto", "bf16x3", "f16f8"],
+                    help="operand arithmetic (include/sce.h sce_arith); auto = f16f8 where the shape allows")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-alt", action="store_true", help="skip the informational single-pass-backward run")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -258,7 +261,7 @@ def main():
     # every rank owns its own shard of the sweep: same shapes, different seeds (model-axis sharding)
     sig = S.TopKEncoder if args.workload == "cfg3" else S.FunctionalTiedSAE
     ens = S.FunctionalEnsemble(make_models(sig, M, d, n, seed=rank), sig, S.adam,
-                               {"lr": 1e-3}, device=dev, bwd_passes=args.bwd_passes)
+                               {"lr": 1e-3}, device=dev, bwd_passes=args.bwd_passes, arith=args.arith)
     n_pool = 8
     host = synth_batches(n_pool, B, d, seed=1000, pin=True)        # identical stream on every rank
     pool = [x.to(dev) for x in host]                                 # resident copies for the device-timed run
@@ -312,10 +315,10 @@ def main():
 
     # ---------------- informational: the same workload with single-pass bf16 backward GEMMs (NOT the headline)
     ms_alt = float("nan")
-    if world == 1 and args.bwd_passes == 3 and sig is S.FunctionalTiedSAE:
+    if world == 1 and args.bwd_passes == 3 and sig is S.FunctionalTiedSAE and not args.no_alt:
         del pool[4:]
         alt = S.FunctionalEnsemble(make_models(S.FunctionalTiedSAE, M, d, n, seed=rank), S.FunctionalTiedSAE, S.adam,
-                                   {"lr": 1e-3}, device=dev, bwd_passes=1)
+                                   {"lr": 1e-3}, device=dev, bwd_passes=1, arith=args.arith)
         for i in range(3):
             alt.step_batch(pool[i % len(pool)])
         e4, e5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -339,6 +342,18 @@ def main():
 
     if rank == 0:
         pk = peaks()
+        arith = ens.resolved_arith()
+        # tensor work issued per fp32-equivalent GEMM, in bf16-pass equivalents: three kind::f16 passes, or one
+        # kind::f16 pass + two kind::f8f6f4 passes at twice the rate
+        full_passes = 3 if arith == "bf16x3" else 2
+        bwd_eq = full_passes if args.bwd_passes == 3 else 1
+        arith_text = {
+            "bf16x3": "fp32 parameters/moments/accumulation; every GEMM operand is an exact-to-2^-17 (hi, lo) bf16 pair "
+                      "and every product 3 tensor-core passes (hi*hi + hi*lo + lo*hi)",
+            "f16f8": "fp32 parameters/moments/accumulation; every GEMM operand is an fp16 plane plus two e5m2 planes "
+                     "(value, scaled residual); every product = one kind::f16 pass (h*h) + two kind::f8f6f4 passes for "
+                     "the cross terms (2 bf16-pass equivalents), rescaled in the accumulator",
+        }[arith] + "; parity <= 1e-4 rel vs the fp32 reference on x_hat and losses"
         value = world * B * K / (ms * 1e-3)
         e2e_value = world * B * K / (ms_e2e * 1e-3)
         steps_prof = max(phases["steps"], 1)
@@ -354,9 +369,7 @@ def main():
             "data": "synthetic",
             "config": {"workload": f"{args.workload}: {desc}", "models_per_gpu": M, "d_model": d, "dict_size": n,
                        "batch": B, "parallelism": f"ensemble-shard x{world}" if world > 1 else "single GPU",
-                       "arithmetic": "fp32 parameters/moments/accumulation; every GEMM operand is an exact-to-2^-17 "
-                                     "(hi, lo) bf16 pair and every product 3 tensor-core passes (hi*hi + hi*lo + lo*hi), "
-                                     "parity <= 1e-4 rel vs the fp32 reference on x_hat and losses",
+                       "arith": arith, "arithmetic": arith_text, "pass_equivalents_per_gemm": full_passes,
                        "fwd_passes": 3, "bwd_passes": args.bwd_passes, "adam_count_mode": "frozen_t1",
                        "l2": "per-step working set (code + code-gradient, 4.3 GB) and the 8-batch input pool "
                              "(134 MB) both exceed the 126 MB L2; no explicit flush"},
@@ -368,15 +381,15 @@ def main():
                          "frac": achieved / pk["bf16_tflops"] if achieved else None, "traffic": None,
                          "peak_source": pk["source"], "alg_flops_per_launch": alg_flops_dw,
                          "ms_per_launch": dw_ms,
-                         "issued_tflops": alg_flops_dw * args.bwd_passes / (dw_ms * 1e-3) / 1e12 if dw_ms > 0 else None,
+                         "issued_tflops": alg_flops_dw * bwd_eq / (dw_ms * 1e-3) / 1e12 if dw_ms > 0 else None,
                          "step_alg_tflops": step_flops / (ms / K * 1e-3) / 1e12},
             "phases_ms": per_phase,
             # every GEMM phase against the same peak: algorithmic (fp32-equivalent) and issued (x passes) TFLOP/s
             "gemms": {ph: {"alg_tflops": units * 2.0 * M * B * n * d / (per_phase[ph] * 1e-3) / 1e12,
                            "issued_tflops": units * 2.0 * M * B * n * d * passes / (per_phase[ph] * 1e-3) / 1e12,
                            "frac_of_peak_issued": units * 2.0 * M * B * n * d * passes / (per_phase[ph] * 1e-3) / 1e12 / pk["bf16_tflops"]}
-                      for ph, units, passes in (("encode", 1, 3), ("decode", 1, 3), ("dcode", 1, args.bwd_passes),
-                                                ("dw", 2, args.bwd_passes)) if per_phase[ph] > 0},
+                      for ph, units, passes in (("encode", 1, full_passes), ("decode", 1, full_passes), ("dcode", 1, bwd_eq),
+                                                ("dw", 2, bwd_eq)) if per_phase[ph] > 0},
             "final_loss_mean": float(final_loss.mean()),
         }
         tr = ncu_traffic()
@@ -385,8 +398,8 @@ def main():
             line["roofline"]["traffic_source"] = tr["source"]
             line["roofline"]["alg_bytes_per_launch"] = 2 * 4.0 * M * B * n + 4.0 * M * n * d   # dz,c (hi,lo) + dW
         if ms_alt == ms_alt:
-            line["alt_precision"] = {"note": "informational only: backward GEMMs as single-pass bf16 (bwd_passes=1); "
-                                             "forward, losses and x̂ unchanged (3-pass)",
+            line["alt_precision"] = {"note": "informational only: backward GEMMs on the 16-bit plane alone (bwd_passes=1); "
+                                             "forward, losses and x̂ unchanged",
                                      "value": B * K / (ms_alt * 1e-3), "ms_per_step": ms_alt / K}
         if world == 1 and not args.no_cpu_baseline:
             rate, sample, cores, _ = cpu_reference_rate(M, d, n, B, budget_s=20.0)

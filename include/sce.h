@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define SCE_VERSION 100 /* major*10000 + minor*100 + patch */
+#define SCE_VERSION 101 /* major*10000 + minor*100 + patch */
 
 typedef enum sce_status {
   SCE_OK = 0,
@@ -45,6 +45,17 @@ typedef enum sce_adam_count {
   SCE_ADAM_STANDARD = 1   /* bias correction with the true step number */
 } sce_adam_count;
 
+/* How an fp32 GEMM operand is carried to the tensor cores. Both reach the reference's fp32
+ * results within the 1e-4 bar; they differ in cost and in the range of values they can hold.
+ *   BF16X3: x = hi + lo, two bf16 planes; product = hi*hi + hi*lo + lo*hi, three kind::f16 passes. fp32 range.
+ *   F16F8 : x = h + l, h = fp16(x); the dominant h*h runs as one kind::f16 pass, the two cross terms (which need
+ *           ~3 significant bits) as kind::f8f6f4 E5M2 passes at twice the rate: 2 pass-equivalents instead of 3.
+ *           Operand values must fit fp16 (|v| < 65504; magnitudes below ~1e-4 lose relative precision) — true for
+ *           language-model activations, which the reference itself stores as fp16 (activation_dataset.py:294-299, 364, 404-412).
+ *           Needs d % 16 == 0 and n % 16 == 0.
+ *   AUTO  : F16F8 when the shape allows it, else BF16X3 (env SCE_ARITH=bf16x3|f16f8 overrides AUTO). */
+typedef enum sce_arith { SCE_ARITH_AUTO = 0, SCE_ARITH_BF16X3 = 1, SCE_ARITH_F16F8 = 2 } sce_arith;
+
 /* Static description of one stacked ensemble (FunctionalEnsemble.__init__, ensemble.py:69-97). */
 typedef struct sce_desc {
   int variant;          /* sce_variant */
@@ -55,9 +66,10 @@ typedef struct sce_desc {
   int x_per_model;      /* 0: one [B,d] batch shared by all models (expand_dims=True); 1: [M,B,d] */
   float lr, beta1, beta2, eps, eps_root; /* torchopt.adam hyper-parameters */
   int adam_count_mode;  /* sce_adam_count */
-  int fwd_passes;       /* 3: split-bf16 (hi*hi+hi*lo+lo*hi, ~fp32 accuracy; default), 1: plain bf16 */
+  int fwd_passes;       /* 3: split operands (~fp32 accuracy; default), 1: the 16-bit plane only (bf16 or fp16) */
   int bwd_passes;       /* same for the three backward GEMMs */
   float norm_floor;     /* clamp floor of the row norms: 1e-8 (SAE variants); <= 0 disables it (TopK) */
+  int arith;            /* enum sce_arith; 0 = AUTO */
 } sce_desc;
 
 /* Device pointers owned by the caller; all fp32 unless noted. Unused ones are NULL. */
@@ -154,6 +166,9 @@ int sce_set_step_count(sce_plan* plan, long long steps_taken);
 
 /* Number of kernels the most recent sce_step / sce_forward on this plan launched. */
 int sce_last_launch_count(const sce_plan* plan);
+
+/* The arithmetic the plan resolved to: SCE_ARITH_BF16X3 or SCE_ARITH_F16F8. */
+int sce_plan_arith(const sce_plan* plan);
 
 #ifdef __cplusplus
 }

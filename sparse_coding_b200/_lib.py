@@ -14,12 +14,16 @@ LIB_PATH = os.path.join(_HERE, "libsce.so")
 SCE_TIED, SCE_UNTIED, SCE_TOPK = 0, 1, 2
 SCE_ADAM_FROZEN_T1, SCE_ADAM_STANDARD = 0, 1
 SCE_LOSS_COLS = 4
+SCE_ARITH_AUTO, SCE_ARITH_BF16X3, SCE_ARITH_F16F8 = 0, 1, 2
+ARITH_CODE = {"auto": SCE_ARITH_AUTO, "bf16x3": SCE_ARITH_BF16X3, "f16f8": SCE_ARITH_F16F8}
+ARITH_NAME = {SCE_ARITH_BF16X3: "bf16x3", SCE_ARITH_F16F8: "f16f8"}
 
 # every symbol include/sce.h declares (tests check that the built library exports all of them)
 EXPORTS = [
     "sce_version", "sce_last_error", "sce_workspace_bytes", "sce_plan_create", "sce_plan_destroy", "sce_prepare",
     "sce_step", "sce_step_host", "sce_forward", "sce_read_code", "sce_grads", "sce_gather_rows",
     "sce_last_launch_count", "sce_get_step_count", "sce_set_step_count", "sce_profile_begin", "sce_profile_end",
+    "sce_plan_arith",
 ]
 PHASES = ["split", "encode", "decode", "losses", "dcode", "dw", "adam"]
 
@@ -30,6 +34,7 @@ class SceDesc(C.Structure):
         ("x_per_model", C.c_int),
         ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float), ("eps_root", C.c_float),
         ("adam_count_mode", C.c_int), ("fwd_passes", C.c_int), ("bwd_passes", C.c_int), ("norm_floor", C.c_float),
+        ("arith", C.c_int),
     ]
 
 
@@ -80,6 +85,7 @@ def load():
     lib.sce_set_step_count.argtypes = [vp, ll]
     lib.sce_profile_begin.argtypes = [vp]
     lib.sce_profile_end.argtypes = [vp, vp, vp]
+    lib.sce_plan_arith.argtypes = [vp]
     for name in EXPORTS:
         getattr(lib, name)  # AttributeError here means header and library disagree
     _lib = lib

@@ -43,12 +43,13 @@ static int fail(int code, const char* fmt, ...) {
 // ------------------------------------------------------------------------------------------------
 // plan
 // ------------------------------------------------------------------------------------------------
-struct GemmMaps {  // tensor maps of one GEMM for one batch size
+struct GemmMaps {  // tensor maps of one GEMM for one batch size (x8: third plane of the f16f8 arithmetic)
   CUtensorMap a_hi[kMaxSets], a_lo[kMaxSets], b_hi[kMaxSets], b_lo[kMaxSets];
+  CUtensorMap a_x8[kMaxSets], b_x8[kMaxSets];
 };
 struct BatchMaps {
   GemmMaps encode, decode, dcode, dw_enc, dw_dec;
-  CUtensorMap st_c_hi, st_c_lo, st_dz_hi, st_dz_lo;  // epilogue TMA-store maps
+  CUtensorMap st_c_hi, st_c_lo, st_c_x8, st_dz_hi, st_dz_lo, st_dz_x8;  // epilogue TMA-store maps
   cudaGraphExec_t graph;       // captured step for this batch size (launch-bound shapes), or nullptr
   float *graph_losses, *graph_nnz;
   int graph_launches, eager_steps;
@@ -61,12 +62,16 @@ struct sce_plan {
   int device;  // CUDA device the plan was created on (the caller keeps it current for every call)
   int xm;  // number of distinct input batches (1 shared, or M)
   // workspace carve-up
+  // Operand planes. bf16x3: hi, lo = bf16 planes (2 B / element each), x8 unused. f16f8: hi = fp16 plane, lo =
+  // e5m2 plane of the values, x8 = e5m2 plane of the scaled residuals (1 B / element each): 4 B / element either way.
+  int arith;                      // kArithBf16x3 or kArithF16F8 (resolved from desc.arith / env SCE_ARITH / the shape)
   float* x_stage;                 // [xm, Bmax, d] staging for host-fed steps
   __nv_bfloat16 *x_hi, *x_lo;     // [xm, Bmax, d]
   __nv_bfloat16 *wenc_hi, *wenc_lo, *wdec_hi, *wdec_lo;  // [M, n, d] (tied: dec aliases enc)
   __nv_bfloat16 *c_hi, *c_lo;     // [M, Bmax, n]
   __nv_bfloat16 *g_hi, *g_lo;     // [M, Bmax, d]
-  __nv_bfloat16 *dz_hi, *dz_lo;   // [M, Bmax, n]   (top-k: fp32 scores alias this pair)
+  __nv_bfloat16 *dz_hi, *dz_lo;   // [M, Bmax, n]   (top-k: fp32 scores alias these planes)
+  uint8_t *x_x8, *wenc_x8, *wdec_x8, *c_x8, *g_x8, *dz_x8;
   float *dw_enc, *dw_dec;         // [M, n, d]
   float *part_enc, *part_dec, *db_part, *bnorm, *l1_over_b, *loss_stage, *nnz_stage;
   int tiles_mB_max;
@@ -114,7 +119,24 @@ static int validate(const sce_desc* d) {
   if (d->d > 2048) return fail(SCE_ERR_INVALID, "d = %d > 2048 is not supported by the row kernels", d->d);
   if ((d->fwd_passes != 1 && d->fwd_passes != 3) || (d->bwd_passes != 1 && d->bwd_passes != 3))
     return fail(SCE_ERR_INVALID, "fwd_passes / bwd_passes must be 1 or 3");
+  if (d->arith < SCE_ARITH_AUTO || d->arith > SCE_ARITH_F16F8) return fail(SCE_ERR_INVALID, "unknown arith %d", d->arith);
+  if (d->arith == SCE_ARITH_F16F8 && (d->d % 16 || d->n % 16))
+    return fail(SCE_ERR_INVALID, "arith = F16F8 needs d (%d) and n (%d) to be multiples of 16 (TMA pitch of the 8-bit planes)",
+                d->d, d->n);
   return SCE_OK;
+}
+
+// desc.arith -> kArithBf16x3 / kArithF16F8. AUTO: f16f8 where the 8-bit planes can be addressed by TMA
+// (row pitches of 16 bytes), bf16x3 otherwise; the environment may pin AUTO to one of them (A/B runs).
+static int resolve_arith(const sce_desc& d) {
+  if (d.arith == SCE_ARITH_BF16X3) return kArithBf16x3;
+  if (d.arith == SCE_ARITH_F16F8) return kArithF16F8;
+  const bool shape_ok = d.d % 16 == 0 && d.n % 16 == 0;
+  if (const char* v = getenv("SCE_ARITH")) {
+    if (!strcmp(v, "bf16x3")) return kArithBf16x3;
+    if (!strcmp(v, "f16f8") && shape_ok) return kArithF16F8;
+  }
+  return shape_ok ? kArithF16F8 : kArithBf16x3;
 }
 
 // Carves the workspace; with base == nullptr only measures it.
@@ -125,21 +147,29 @@ static size_t carve(sce_plan* p, const sce_desc& d, uint8_t* base) {
   const size_t tiles_mB = (B + kBM - 1) / kBM;
   const size_t tiles_nN = (n + 127) / 128;  // upper bound over the BN choices (BN >= 128)
   const size_t tiles_nD = (dd + 127) / 128;
+  const bool f8 = resolve_arith(d) == kArithF16F8;
+  // the planes of one operand tensor: 16-bit, then (bf16x3) a second 16-bit plane or (f16f8) two 8-bit planes
+  auto planes = [&](size_t count, __nv_bfloat16*& hi, __nv_bfloat16*& lo, uint8_t*& x8) {
+    hi = c.take<__nv_bfloat16>(count);
+    if (f8) {
+      lo = reinterpret_cast<__nv_bfloat16*>(c.take<uint8_t>(count));
+      x8 = c.take<uint8_t>(count);
+    } else {
+      lo = c.take<__nv_bfloat16>(count);
+      x8 = nullptr;
+    }
+  };
   auto X = c.take<float>(xm * B * dd);
-  auto xh = c.take<__nv_bfloat16>(xm * B * dd);
-  auto xl = c.take<__nv_bfloat16>(xm * B * dd);
-  auto weh = c.take<__nv_bfloat16>(M * n * dd);
-  auto wel = c.take<__nv_bfloat16>(M * n * dd);
+  __nv_bfloat16 *xh, *xl, *weh, *wel, *ch, *cl, *gh, *gl;
+  uint8_t *x8, *we8, *c8, *g8;
+  planes(xm * B * dd, xh, xl, x8);
+  planes(M * n * dd, weh, wel, we8);
   __nv_bfloat16 *wdh = weh, *wdl = wel;
-  if (d.variant == SCE_UNTIED) {
-    wdh = c.take<__nv_bfloat16>(M * n * dd);
-    wdl = c.take<__nv_bfloat16>(M * n * dd);
-  }
-  auto ch = c.take<__nv_bfloat16>(M * B * n);
-  auto cl = c.take<__nv_bfloat16>(M * B * n);
-  auto gh = c.take<__nv_bfloat16>(M * B * dd);
-  auto gl = c.take<__nv_bfloat16>(M * B * dd);
-  auto dzh = c.take<__nv_bfloat16>(2 * M * B * n);  // hi then lo, contiguous: 4 B / element in total
+  uint8_t* wd8 = we8;
+  if (d.variant == SCE_UNTIED) planes(M * n * dd, wdh, wdl, wd8);
+  planes(M * B * n, ch, cl, c8);
+  planes(M * B * dd, gh, gl, g8);
+  auto dzh = c.take<__nv_bfloat16>(2 * M * B * n);  // all planes contiguous, 4 B / element: the top-k scores alias them
   auto dwe = c.take<float>(M * n * dd);
   float* dwd = dwe;
   if (d.variant == SCE_UNTIED) dwd = c.take<float>(M * n * dd);
@@ -165,6 +195,12 @@ static size_t carve(sce_plan* p, const sce_desc& d, uint8_t* base) {
     p->g_lo = gl;
     p->dz_hi = dzh;
     p->dz_lo = dzh + M * B * n;
+    p->dz_x8 = f8 ? reinterpret_cast<uint8_t*>(dzh) + 3 * M * B * n : nullptr;
+    p->x_x8 = x8;
+    p->wenc_x8 = we8;
+    p->wdec_x8 = wd8;
+    p->c_x8 = c8;
+    p->g_x8 = g8;
     p->dw_enc = dwe;
     p->dw_dec = dwd;
     p->part_enc = pe;
@@ -205,16 +241,34 @@ static CUtensorMapSwizzle swizzle_for_bk(int bk) {
   return bk == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
 }
 
-// dictionary operand [M][n][d]; `kmajor`: box = [box_rows][kBkK] with the K-major swizzle, else [box_rows][64]
-static bool map2(CUtensorMap* hi, CUtensorMap* lo, const void* phi, const void* plo, uint64_t models,
-                 uint64_t rows, uint64_t cols, uint32_t box_rows, int kmajor_bk) {
-  if (kmajor_bk)
-    return make_tmap_bf16_box(hi, phi, models, rows, cols, cols, rows * cols, kmajor_bk, box_rows,
-                              swizzle_for_bk(kmajor_bk)) &&
-           make_tmap_bf16_box(lo, plo, models, rows, cols, cols, rows * cols, kmajor_bk, box_rows,
-                              swizzle_for_bk(kmajor_bk));
-  return make_tmap_bf16(hi, phi, models, rows, cols, cols, rows * cols, box_rows) &&
-         make_tmap_bf16(lo, plo, models, rows, cols, cols, rows * cols, box_rows);
+static CUtensorMapSwizzle swizzle8_for_bk(int bk) {  // K-major 8-bit tiles: rows of bk bytes
+  return bk == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_64B;
+}
+constexpr int kBkF8 = 64;  // K block of every GEMM in the f16f8 arithmetic
+
+// The planes of one operand [models][rows][cols] (cols contiguous, `mpitch` elements between models) as GEMM operand
+// maps. kmajor_bk != 0: K-major tiles [box_rows][kmajor_bk]; else MN-major tiles of `box_rows` k-rows by 64 (16-bit)
+// / 128 (8-bit) contiguous elements.
+static bool operand_maps(int arith, CUtensorMap* hi, CUtensorMap* lo, CUtensorMap* x8, const void* phi, const void* plo,
+                         const void* px8, uint64_t models, uint64_t rows, uint64_t cols, uint64_t mpitch,
+                         uint32_t box_rows, int kmajor_bk) {
+  bool ok;
+  if (kmajor_bk) {
+    ok = make_tmap_bf16_box(hi, phi, models, rows, cols, cols, mpitch, kmajor_bk, box_rows, swizzle_for_bk(kmajor_bk));
+    if (arith == kArithF16F8)
+      ok = ok && make_tmap_u8_box(lo, plo, models, rows, cols, cols, mpitch, kmajor_bk, box_rows, swizzle8_for_bk(kmajor_bk)) &&
+           make_tmap_u8_box(x8, px8, models, rows, cols, cols, mpitch, kmajor_bk, box_rows, swizzle8_for_bk(kmajor_bk));
+    else
+      ok = ok && make_tmap_bf16_box(lo, plo, models, rows, cols, cols, mpitch, kmajor_bk, box_rows, swizzle_for_bk(kmajor_bk));
+  } else {
+    ok = make_tmap_bf16(hi, phi, models, rows, cols, cols, mpitch, box_rows);
+    if (arith == kArithF16F8)
+      ok = ok && make_tmap_u8_box(lo, plo, models, rows, cols, cols, mpitch, 128, box_rows, CU_TENSOR_MAP_SWIZZLE_128B) &&
+           make_tmap_u8_box(x8, px8, models, rows, cols, cols, mpitch, 128, box_rows, CU_TENSOR_MAP_SWIZZLE_128B);
+    else
+      ok = ok && make_tmap_bf16(lo, plo, models, rows, cols, cols, mpitch, box_rows);
+  }
+  return ok;
 }
 
 static int build_maps(sce_plan* p, int B, BatchMaps** out) {
@@ -230,45 +284,62 @@ static int build_maps(sce_plan* p, int B, BatchMaps** out) {
   const uint64_t M = d.n_models, n = d.n, dd = d.d, xm = p->xm, Bm = d.batch_max;
   // NOTE: activations are laid out with the plan's batch_max pitch between models; only `B` rows are
   // visible through the map, so rows >= B read as zero (TMA out-of-bounds fill).
-  auto act = [&](CUtensorMap* hi, CUtensorMap* lo, const void* phi, const void* plo, uint64_t models,
-                 uint64_t cols, uint32_t box_rows) {   // MN-major use: box = [box_rows k][64]
-    return make_tmap_bf16(hi, phi, models, (uint64_t)B, cols, cols, Bm * cols, box_rows) &&
-           make_tmap_bf16(lo, plo, models, (uint64_t)B, cols, cols, Bm * cols, box_rows);
+  const int ar = p->arith;
+  const bool f8 = ar == kArithF16F8;
+  const int bk_enc = f8 ? kBkF8 : p->bk_encode, bk_dec = f8 ? kBkF8 : p->bk_decode, bk_dco = f8 ? kBkF8 : p->bk_dcode;
+  const int bk_dw = f8 ? kBkF8 : kBkDw;
+  // the f16f8 kernels run narrow outputs (<= 128 columns) on single CTAs: an MN-major 8-bit B tile is 128 wide
+  auto pair_ok = [&](int flag, int rows, int out_cols) { return use_pair(flag, rows) && !(f8 && out_cols <= 128); };
+  struct Pl { const void *hi, *lo, *x8; };
+  const Pl X{p->x_hi, p->x_lo, p->x_x8}, WE{p->wenc_hi, p->wenc_lo, p->wenc_x8}, WD{p->wdec_hi, p->wdec_lo, p->wdec_x8},
+      C{p->c_hi, p->c_lo, p->c_x8}, G{p->g_hi, p->g_lo, p->g_x8}, DZ{p->dz_hi, p->dz_lo, p->dz_x8};
+  // activations [models][B of batch_max][cols]: K-major A tiles [128 rows][bk] / MN-major tiles of bk_dw batch rows
+  auto actk = [&](GemmMaps& g, int set, const Pl& P, uint64_t models, uint64_t cols, int bk) {
+    return operand_maps(ar, &g.a_hi[set], &g.a_lo[set], &g.a_x8[set], P.hi, P.lo, P.x8, models, (uint64_t)B, cols, Bm * cols, kBM, bk);
   };
-  auto actk = [&](CUtensorMap* hi, CUtensorMap* lo, const void* phi, const void* plo, uint64_t models,
-                  uint64_t cols, int bk) {              // K-major A operand: box = [128 rows][bk]
-    return make_tmap_bf16_box(hi, phi, models, (uint64_t)B, cols, cols, Bm * cols, bk, kBM, swizzle_for_bk(bk)) &&
-           make_tmap_bf16_box(lo, plo, models, (uint64_t)B, cols, cols, Bm * cols, bk, kBM, swizzle_for_bk(bk));
+  auto act_a = [&](GemmMaps& g, int set, const Pl& P, uint64_t models, uint64_t cols) {
+    return operand_maps(ar, &g.a_hi[set], &g.a_lo[set], &g.a_x8[set], P.hi, P.lo, P.x8, models, (uint64_t)B, cols, Bm * cols, bk_dw, 0);
+  };
+  auto act_b = [&](GemmMaps& g, int set, const Pl& P, uint64_t models, uint64_t cols) {
+    return operand_maps(ar, &g.b_hi[set], &g.b_lo[set], &g.b_x8[set], P.hi, P.lo, P.x8, models, (uint64_t)B, cols, Bm * cols, bk_dw, 0);
+  };
+  // dictionary [M][n][d] as the B operand: K-major tiles [box_rows][bk] (box_rows = the B rows ONE CTA loads), or MN-major
+  auto dict_b = [&](GemmMaps& g, const Pl& P, uint32_t box_rows, int kmajor_bk) {
+    return operand_maps(ar, &g.b_hi[0], &g.b_lo[0], &g.b_x8[0], P.hi, P.lo, P.x8, M, n, dd, n * dd, box_rows, kmajor_bk);
   };
   bool ok = true;
   // encode: A = x [xm,B,d] K-major, B = Wenc [M,n,d] K-major
-  ok &= actk(&m->encode.a_hi[0], &m->encode.a_lo[0], p->x_hi, p->x_lo, xm, dd, p->bk_encode);
-  // (K-major B tiles are loaded whole by a single CTA, in halves by the two CTAs of a pair)
-  ok &= map2(&m->encode.b_hi[0], &m->encode.b_lo[0], p->wenc_hi, p->wenc_lo, M, n, dd,
-             bn_for(d.n) / (use_pair(p->pair_encode, B) ? 2 : 1), p->bk_encode);
-  // decode: A = c [M,B,n] K-major, B = Wdec [M,n,d] MN-major (box = 64 k-rows x 64 columns)
-  ok &= actk(&m->decode.a_hi[0], &m->decode.a_lo[0], p->c_hi, p->c_lo, M, n, p->bk_decode);
-  ok &= map2(&m->decode.b_hi[0], &m->decode.b_lo[0], p->wdec_hi, p->wdec_lo, M, n, dd, p->bk_decode, 0);
+  ok &= actk(m->encode, 0, X, xm, dd, bk_enc);
+  ok &= dict_b(m->encode, WE, bn_for(d.n) / (pair_ok(p->pair_encode, B, d.n) ? 2 : 1), bk_enc);
+  // decode: A = c [M,B,n] K-major, B = Wdec [M,n,d] MN-major (bk k-rows per box)
+  ok &= actk(m->decode, 0, C, M, n, bk_dec);
+  ok &= dict_b(m->decode, WD, bk_dec, 0);
   // dcode: A = g [M,B,d] K-major, B = Wdec K-major
-  ok &= actk(&m->dcode.a_hi[0], &m->dcode.a_lo[0], p->g_hi, p->g_lo, M, dd, p->bk_dcode);
-  ok &= map2(&m->dcode.b_hi[0], &m->dcode.b_lo[0], p->wdec_hi, p->wdec_lo, M, n, dd,
-             bn_for(d.n) / (use_pair(p->pair_dcode, B) ? 2 : 1), p->bk_dcode);
+  ok &= actk(m->dcode, 0, G, M, dd, bk_dco);
+  ok &= dict_b(m->dcode, WD, bn_for(d.n) / (pair_ok(p->pair_dcode, B, d.n) ? 2 : 1), bk_dco);
   // weight gradients: everything MN-major, reduction over the batch rows
   if (d.variant == SCE_UNTIED) {
-    ok &= act(&m->dw_enc.a_hi[0], &m->dw_enc.a_lo[0], p->dz_hi, p->dz_lo, M, n, kBkDw);
-    ok &= act(&m->dw_enc.b_hi[0], &m->dw_enc.b_lo[0], p->x_hi, p->x_lo, xm, dd, kBkDw);
-    ok &= act(&m->dw_dec.a_hi[0], &m->dw_dec.a_lo[0], p->c_hi, p->c_lo, M, n, kBkDw);
-    ok &= act(&m->dw_dec.b_hi[0], &m->dw_dec.b_lo[0], p->g_hi, p->g_lo, M, dd, kBkDw);
+    ok &= act_a(m->dw_enc, 0, DZ, M, n);
+    ok &= act_b(m->dw_enc, 0, X, xm, dd);
+    ok &= act_a(m->dw_dec, 0, C, M, n);
+    ok &= act_b(m->dw_dec, 0, G, M, dd);
   } else {
-    ok &= act(&m->dw_enc.a_hi[0], &m->dw_enc.a_lo[0], p->dz_hi, p->dz_lo, M, n, kBkDw);
-    ok &= act(&m->dw_enc.b_hi[0], &m->dw_enc.b_lo[0], p->x_hi, p->x_lo, xm, dd, kBkDw);
-    ok &= act(&m->dw_enc.a_hi[1], &m->dw_enc.a_lo[1], p->c_hi, p->c_lo, M, n, kBkDw);
-    ok &= act(&m->dw_enc.b_hi[1], &m->dw_enc.b_lo[1], p->g_hi, p->g_lo, M, dd, kBkDw);
+    ok &= act_a(m->dw_enc, 0, DZ, M, n);
+    ok &= act_b(m->dw_enc, 0, X, xm, dd);
+    ok &= act_a(m->dw_enc, 1, C, M, n);
+    ok &= act_b(m->dw_enc, 1, G, M, dd);
   }
   ok &= make_tmap_bf16_store32(&m->st_c_hi, p->c_hi, M, (uint64_t)B, n, Bm * n);
-  ok &= make_tmap_bf16_store32(&m->st_c_lo, p->c_lo, M, (uint64_t)B, n, Bm * n);
   ok &= make_tmap_bf16_store32(&m->st_dz_hi, p->dz_hi, M, (uint64_t)B, n, Bm * n);
-  ok &= make_tmap_bf16_store32(&m->st_dz_lo, p->dz_lo, M, (uint64_t)B, n, Bm * n);
+  if (f8) {
+    auto st8 = [&](CUtensorMap* t, const void* base) {
+      return make_tmap_u8_box(t, base, M, (uint64_t)B, n, n, Bm * n, 32, 32, CU_TENSOR_MAP_SWIZZLE_32B);
+    };
+    ok &= st8(&m->st_c_lo, p->c_lo) && st8(&m->st_c_x8, p->c_x8) && st8(&m->st_dz_lo, p->dz_lo) && st8(&m->st_dz_x8, p->dz_x8);
+  } else {
+    ok &= make_tmap_bf16_store32(&m->st_c_lo, p->c_lo, M, (uint64_t)B, n, Bm * n);
+    ok &= make_tmap_bf16_store32(&m->st_dz_lo, p->dz_lo, M, (uint64_t)B, n, Bm * n);
+  }
   if (!ok) {
     delete m;
     return fail(SCE_ERR_CUDA, "cuTensorMapEncodeTiled failed (B=%d, M=%d, n=%d, d=%d)", B, d.n_models, d.n, d.d);
@@ -281,12 +352,13 @@ static int build_maps(sce_plan* p, int B, BatchMaps** out) {
 // ------------------------------------------------------------------------------------------------
 // GEMM launcher
 // ------------------------------------------------------------------------------------------------
-template <class Epi, int BN, int BK, bool A_MN, bool B_MN, int STAGES, bool SPLIT_ACC = false, bool CTA2 = false>
+template <class Epi, int BN, int BK, bool A_MN, bool B_MN, int STAGES, bool SPLIT_ACC = false, bool CTA2 = false,
+          int ARITH = kArithBf16x3>
 static int launch_gemm_t(const sce_plan* p, const GemmMaps& maps, int nsets, const int* a_batched,
                          const int* b_batched, int k_total, int passes, int m_total, int n_total,
                          const typename Epi::Params& epi, cudaStream_t st) {
-  using SM = GemmSmem<BN, BK, A_MN, B_MN, STAGES, Epi::kWarpStageBytes, CTA2>;
-  auto kern = gemm_split_kernel<Epi, BN, BK, A_MN, B_MN, STAGES, SPLIT_ACC, CTA2>;
+  using SM = GemmSmem<BN, BK, A_MN, B_MN, STAGES, Epi::kWarpStageBytes, CTA2, ARITH>;
+  auto kern = gemm_split_kernel<Epi, BN, BK, A_MN, B_MN, STAGES, SPLIT_ACC, CTA2, ARITH>;
   // the opt-in to > 48 KB of dynamic shared memory is per device: remember which devices have it
   static bool configured[64] = {};
   if (p->device < 0 || p->device >= 64 || !configured[p->device]) {
@@ -300,6 +372,8 @@ static int launch_gemm_t(const sce_plan* p, const GemmMaps& maps, int nsets, con
     gp.a_lo[s] = maps.a_lo[s];
     gp.b_hi[s] = maps.b_hi[s];
     gp.b_lo[s] = maps.b_lo[s];
+    gp.a_x8[s] = maps.a_x8[s];
+    gp.b_x8[s] = maps.b_x8[s];
     gp.a_batched[s] = a_batched[s];
     gp.b_batched[s] = b_batched[s];
   }
@@ -333,8 +407,17 @@ static int launch_gemm_t(const sce_plan* p, const GemmMaps& maps, int nsets, con
 
 // Dispatch a K-major-A GEMM on (output width -> BN, K block, single CTA or CTA pair). Stage counts fill the
 // 192 KB operand ring: single 256x{64,32} -> 2,4; 128x{64,32} -> 3,6; pair 256x{64,32} -> 3,6; 128x{64,32} -> 4,8.
-template <class Epi, bool B_MN, bool SPLIT, class... Args>
+// f16f8: K block 64 everywhere, a stage is one 16-bit plane of A and of B (or their four 8-bit planes): pair
+// 256-wide -> 6 stages of 32 KB, single 256-wide -> 4 of 48 KB, single 128-wide -> 6 of 32 KB; narrow outputs
+// never run on pairs (see build_maps).
+template <class Epi, bool B_MN, bool SPLIT, int ARITH, class... Args>
 static int launch_k(bool wide, int bk, bool pair, Args&&... a) {
+  if constexpr (ARITH == kArithF16F8) {
+    if (wide)
+      return pair ? launch_gemm_t<Epi, 256, kBkF8, false, B_MN, 6, false, true, kArithF16F8>(a...)
+                  : launch_gemm_t<Epi, 256, kBkF8, false, B_MN, 4, false, false, kArithF16F8>(a...);
+    return launch_gemm_t<Epi, 128, kBkF8, false, B_MN, 6, false, false, kArithF16F8>(a...);
+  } else {
   if (wide) {
     if (bk == 32)
       return pair ? launch_gemm_t<Epi, 256, 32, false, B_MN, 6, SPLIT, true>(a...)
@@ -347,6 +430,7 @@ static int launch_k(bool wide, int bk, bool pair, Args&&... a) {
                 : launch_gemm_t<Epi, 128, 32, false, B_MN, 6, SPLIT, false>(a...);
   return pair ? launch_gemm_t<Epi, 128, 64, false, B_MN, 4, SPLIT, true>(a...)
               : launch_gemm_t<Epi, 128, 64, false, B_MN, 3, SPLIT, false>(a...);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -365,19 +449,37 @@ static AdamHyper hyper_for(const sce_plan* p, long long t) {
   return h;
 }
 
-template <int MODE>
-static int launch_dict_rows(float* e, const float* dw, float* m, float* v, __nv_bfloat16* hi, __nv_bfloat16* lo,
-                            float* grad_out, long long rows, int d, int normalize, float floor, AdamHyper h,
-                            cudaStream_t st) {
+template <int MODE, int ARITH>
+static int launch_dict_rows_t(float* e, const float* dw, float* m, float* v, void* hi, void* lo, void* x8,
+                              float* grad_out, long long rows, int d, int normalize, float floor, AdamHyper h,
+                              cudaStream_t st) {
   const int nv = (d + 511) / 512;
   if (nv == 1)
-    dict_rows_kernel<1, MODE><<<(unsigned)rows, 128, 0, st>>>(e, dw, m, v, hi, lo, grad_out, d, normalize, floor, h);
+    dict_rows_kernel<1, MODE, ARITH><<<(unsigned)rows, 128, 0, st>>>(e, dw, m, v, hi, lo, x8, grad_out, d, normalize, floor, h);
   else if (nv == 2)
-    dict_rows_kernel<2, MODE><<<(unsigned)rows, 128, 0, st>>>(e, dw, m, v, hi, lo, grad_out, d, normalize, floor, h);
+    dict_rows_kernel<2, MODE, ARITH><<<(unsigned)rows, 128, 0, st>>>(e, dw, m, v, hi, lo, x8, grad_out, d, normalize, floor, h);
   else
-    dict_rows_kernel<4, MODE><<<(unsigned)rows, 128, 0, st>>>(e, dw, m, v, hi, lo, grad_out, d, normalize, floor, h);
+    dict_rows_kernel<4, MODE, ARITH><<<(unsigned)rows, 128, 0, st>>>(e, dw, m, v, hi, lo, x8, grad_out, d, normalize, floor, h);
   CUDA_TRY(cudaGetLastError());
   return SCE_OK;
+}
+// `which`: 0 = the encoder's operand planes, 1 = the decoder's
+template <int MODE>
+static int launch_dict_rows(const sce_plan* p, int which, float* e, const float* dw, float* m, float* v, float* grad_out,
+                            long long rows, int d, int normalize, float floor, AdamHyper h, cudaStream_t st) {
+  void* hi = which ? (void*)p->wdec_hi : (void*)p->wenc_hi;
+  void* lo = which ? (void*)p->wdec_lo : (void*)p->wenc_lo;
+  void* x8 = which ? (void*)p->wdec_x8 : (void*)p->wenc_x8;
+  if (MODE == MODE_GRAD) hi = lo = x8 = nullptr;
+  return p->arith == kArithF16F8
+             ? launch_dict_rows_t<MODE, kArithF16F8>(e, dw, m, v, hi, lo, x8, grad_out, rows, d, normalize, floor, h, st)
+             : launch_dict_rows_t<MODE, kArithBf16x3>(e, dw, m, v, hi, lo, x8, grad_out, rows, d, normalize, floor, h, st);
+}
+
+// f16f8 runs the backward pass on the residual r instead of g = 2r/(B d) (EpiDecodeT): weight- and bias-gradient
+// outputs are multiplied by 2/(B d) on the way out, the sparsity term enters dcode as alpha d / 2.
+static float grad_out_scale(const sce_plan* p, int B) {
+  return p->arith == kArithF16F8 ? 2.0f / ((float)B * (float)p->d.d) : 1.0f;
 }
 
 __global__ void l1_over_b_kernel(const float* __restrict__ alpha, float* __restrict__ out, int M, float invB) {
@@ -386,8 +488,13 @@ __global__ void l1_over_b_kernel(const float* __restrict__ alpha, float* __restr
 }
 
 // forward (+ optional backward GEMMs). Leaves dW in p->dw_enc / p->dw_dec when `backward`.
-static int run_pipeline(sce_plan* p, const float* x, int B, float* x_hat, bool backward, float* out_losses,
-                        float* out_nnz, cudaStream_t st) {
+template <int AR>
+static int run_pipeline_t(sce_plan* p, const float* x, int B, float* x_hat, bool backward, float* out_losses,
+                          float* out_nnz, cudaStream_t st) {
+  using EpiEnc = EpiEncodeT<AR>;
+  using EpiDec = EpiDecodeT<AR>;
+  using EpiDco = EpiDcodeT<AR>;
+  constexpr bool f8 = AR == kArithF16F8;
   const sce_desc& d = p->d;
   if (B < 1 || B > d.batch_max) return fail(SCE_ERR_INVALID, "B = %d outside [1, batch_max = %d]", B, d.batch_max);
   if (!x) return fail(SCE_ERR_INVALID, "x is NULL");
@@ -406,29 +513,36 @@ static int run_pipeline(sce_plan* p, const float* x, int B, float* x_hat, bool b
   for (int m = 0; m < p->xm; ++m) {
     const long long n4 = (long long)B * dd / 4;
     const int blocks = (int)((n4 + 255) / 256 < 2048 ? (n4 + 255) / 256 : 2048);
-    split_rows_kernel<<<blocks, 256, 0, st>>>(x + (long long)m * B * dd, p->x_hi + m * Bm * dd,
-                                              p->x_lo + m * Bm * dd, n4);
+    // (bf16x3: the lo plane is 2 B / element; f16f8: lo and x8 are 1 B / element)
+    split_rows_kernel<AR><<<blocks, 256, 0, st>>>(
+        x + (long long)m * B * dd, p->x_hi + m * Bm * dd,
+        f8 ? (void*)(reinterpret_cast<uint8_t*>(p->x_lo) + m * Bm * dd) : (void*)(p->x_lo + m * Bm * dd),
+        f8 ? (void*)(p->x_x8 + m * Bm * dd) : nullptr, n4);
     ++launches;
   }
   CUDA_TRY(cudaGetLastError());
-  l1_over_b_kernel<<<(M + 127) / 128, 128, 0, st>>>(p->b.l1_alpha, p->l1_over_b, M, 1.0f / (float)B);
+  // alpha / B, or (f16f8, backward on r = g B d / 2) alpha d / 2
+  l1_over_b_kernel<<<(M + 127) / 128, 128, 0, st>>>(p->b.l1_alpha, p->l1_over_b, M, f8 ? 0.5f * (float)dd : 1.0f / (float)B);
   ++launches;
+  // the f16f8 kernels run narrow outputs on single CTAs (build_maps)
+  auto pair_ok = [&](int flag, int rows, int out_cols) { return use_pair(flag, rows) && !(f8 && out_cols <= 128); };
 
   // ---- encode
   prof_mark(p, SCE_PHASE_ENCODE, st);
   int n_enc_parts;
   if (d.variant != SCE_TOPK) {
-    EpiEncode::Params ep;
+    typename EpiEnc::Params ep;
     ep.out_hi = maps->st_c_hi;
     ep.out_lo = maps->st_c_lo;
+    ep.out_x8 = maps->st_c_x8;
     ep.bias = p->b.encoder_bias;
     ep.mask = p->b.coef_mask;
     ep.part = p->part_enc;
     ep.tiles_m = tiles_mB;
     ep.flag_zero = 1;
     ep.tiles_n = n > 128 ? (n + 255) / 256 : 1;
-    rc = launch_k<EpiEncode, false, false>(n > 128, p->bk_encode, use_pair(p->pair_encode, B), p, maps->encode, 1, xb, one,
-                                           dd, d.fwd_passes, B, n, ep, st);
+    rc = launch_k<EpiEnc, false, false, AR>(n > 128, p->bk_encode, pair_ok(p->pair_encode, B, n), p, maps->encode, 1, xb, one,
+                                            dd, d.fwd_passes, B, n, ep, st);
     if (rc) return rc;
     ++launches;
     n_enc_parts = tiles_mB * 8 * ep.tiles_n;
@@ -438,20 +552,22 @@ static int run_pipeline(sce_plan* p, const float* x, int B, float* x_hat, bool b
     sp.out = reinterpret_cast<float*>(p->dz_hi);
     sp.model_stride = Bm * n;
     sp.ld = n;
-    rc = launch_k<EpiStoreF32, false, false>(n > 128, p->bk_encode, use_pair(p->pair_encode, B), p, maps->encode, 1, xb,
-                                             one, dd, d.fwd_passes, B, n, sp, st);
+    sp.scale = 1.f;
+    rc = launch_k<EpiStoreF32, false, false, AR>(n > 128, p->bk_encode, pair_ok(p->pair_encode, B, n), p, maps->encode, 1, xb,
+                                                 one, dd, d.fwd_passes, B, n, sp, st);
     if (rc) return rc;
     ++launches;
     if ((size_t)n * 4 > 200 * 1024) return fail(SCE_ERR_INVALID, "top-k: n = %d exceeds the shared-memory row buffer", n);
     const int use_cand = (size_t)n * 8 <= 200 * 1024;   // keys + candidate list, else keys only
     static bool cfg[64] = {};
     if (p->device < 0 || p->device >= 64 || !cfg[p->device]) {
-      CUDA_TRY(cudaFuncSetAttribute(topk_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      CUDA_TRY(cudaFuncSetAttribute(topk_select_kernel<AR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       if (p->device >= 0 && p->device < 64) cfg[p->device] = true;
     }
     // one block per (row, model); scores / codes of model m start at m * batch_max * n
-    topk_select_kernel<<<dim3(B, M), 256, (size_t)n * (use_cand ? 8 : 4), st>>>(
-        reinterpret_cast<const float*>(p->dz_hi), p->b.sparsity, p->c_hi, p->c_lo, p->part_enc, B, n, Bm * n, use_cand);
+    topk_select_kernel<AR><<<dim3(B, M), 256, (size_t)n * (use_cand ? 8 : 4), st>>>(
+        reinterpret_cast<const float*>(p->dz_hi), p->b.sparsity, p->c_hi, p->c_lo, p->c_x8, p->part_enc, B, n, Bm * n,
+        use_cand);
     ++launches;
     CUDA_TRY(cudaGetLastError());
     n_enc_parts = B;
@@ -459,25 +575,26 @@ static int run_pipeline(sce_plan* p, const float* x, int B, float* x_hat, bool b
 
   // ---- decode (+ residual, loss partial, g)
   prof_mark(p, SCE_PHASE_DECODE, st);
-  EpiDecode::Params dp;
+  typename EpiDec::Params dp;
   dp.x = x;
   dp.x_model_stride = d.x_per_model ? (long long)B * dd : 0;
-  dp.g_hi = p->g_hi;
-  dp.g_lo = p->g_lo;
+  dp.g_hi = reinterpret_cast<uint16_t*>(p->g_hi);
+  dp.g_lo = reinterpret_cast<uint8_t*>(p->g_lo);
+  dp.g_x8 = p->g_x8;
   dp.x_hat = x_hat;
   dp.part = p->part_dec;
   dp.g_model_stride = Bm * dd;
   dp.xhat_model_stride = (long long)B * dd;
   dp.ld = dd;
   dp.tiles_m = tiles_mB;
-  dp.gscale = 2.0f / ((float)B * (float)dd);
+  dp.gscale = f8 ? 1.0f : 2.0f / ((float)B * (float)dd);
   dp.tiles_n = dd > 128 ? (dd + 255) / 256 : 1;
-  if (p->split_decode)
-    rc = launch_k<EpiDecode, true, true>(dd > 128, p->bk_decode, use_pair(p->pair_decode, B), p, maps->decode, 1, one, one,
-                                         n, d.fwd_passes, B, dd, dp, st);
-  else
-    rc = launch_k<EpiDecode, true, false>(dd > 128, p->bk_decode, use_pair(p->pair_decode, B), p, maps->decode, 1, one, one,
+  if (p->split_decode && !f8)
+    rc = launch_k<EpiDec, true, true, AR>(dd > 128, p->bk_decode, pair_ok(p->pair_decode, B, dd), p, maps->decode, 1, one, one,
                                           n, d.fwd_passes, B, dd, dp, st);
+  else
+    rc = launch_k<EpiDec, true, false, AR>(dd > 128, p->bk_decode, pair_ok(p->pair_decode, B, dd), p, maps->decode, 1, one, one,
+                                           n, d.fwd_passes, B, dd, dp, st);
   if (rc) return rc;
   ++launches;
 
@@ -495,17 +612,18 @@ static int run_pipeline(sce_plan* p, const float* x, int B, float* x_hat, bool b
   prof_mark(p, SCE_PHASE_DCODE, st);
   if (backward) {
     // ---- dcode
-    EpiDcode::Params zp;
+    typename EpiDco::Params zp;
     zp.out_hi = maps->st_dz_hi;
     zp.out_lo = maps->st_dz_lo;
+    zp.out_x8 = maps->st_dz_x8;
     zp.c_hi = p->c_hi;
     zp.l1_over_b = p->l1_over_b;
     zp.db_part = p->b.encoder_bias ? p->db_part : nullptr;
     zp.c_model_stride = Bm * n;
     zp.ldc = n;
     zp.tiles_m = tiles_mB;
-    rc = launch_k<EpiDcode, false, false>(n > 128, p->bk_dcode, use_pair(p->pair_dcode, B), p, maps->dcode, 1, one, one, dd,
-                                          p->dcode_passes, B, n, zp, st);
+    rc = launch_k<EpiDco, false, false, AR>(n > 128, p->bk_dcode, pair_ok(p->pair_dcode, B, n), p, maps->dcode, 1, one, one, dd,
+                                            p->dcode_passes, B, n, zp, st);
     if (rc) return rc;
     ++launches;
 
@@ -516,7 +634,14 @@ static int run_pipeline(sce_plan* p, const float* x, int B, float* x_hat, bool b
       sp.out = out;
       sp.model_stride = (long long)n * dd;
       sp.ld = dd;
-      const bool pair = use_pair(p->pair_dw, n);
+      sp.scale = grad_out_scale(p, B);
+      const bool pair = pair_ok(p->pair_dw, n, dd);
+      if constexpr (f8) {
+        if (dd > 128)
+          return pair ? launch_gemm_t<EpiStoreF32, 256, kBkF8, true, true, 6, false, true, kArithF16F8>(p, gm, nsets, ab, bb, B, p->dw_passes, n, dd, sp, st)
+                      : launch_gemm_t<EpiStoreF32, 256, kBkF8, true, true, 4, false, false, kArithF16F8>(p, gm, nsets, ab, bb, B, p->dw_passes, n, dd, sp, st);
+        return launch_gemm_t<EpiStoreF32, 128, kBkF8, true, true, 6, false, false, kArithF16F8>(p, gm, nsets, ab, bb, B, p->dw_passes, n, dd, sp, st);
+      }
       if (dd > 128)
         return pair ? launch_gemm_t<EpiStoreF32, 256, kBkDw, true, true, 6, true, true>(p, gm, nsets, ab, bb, B, p->dw_passes, n, dd, sp, st)
                     : launch_gemm_t<EpiStoreF32, 256, kBkDw, true, true, 4, true, false>(p, gm, nsets, ab, bb, B, p->dw_passes, n, dd, sp, st);
@@ -539,6 +664,12 @@ static int run_pipeline(sce_plan* p, const float* x, int B, float* x_hat, bool b
   prof_mark(p, SCE_PHASE_ADAM, st);
   p->last_launches = launches;
   return SCE_OK;
+}
+
+static int run_pipeline(sce_plan* p, const float* x, int B, float* x_hat, bool backward, float* out_losses,
+                        float* out_nnz, cudaStream_t st) {
+  return p->arith == kArithF16F8 ? run_pipeline_t<kArithF16F8>(p, x, B, x_hat, backward, out_losses, out_nnz, st)
+                                 : run_pipeline_t<kArithBf16x3>(p, x, B, x_hat, backward, out_losses, out_nnz, st);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -586,6 +717,7 @@ int sce_plan_create(const sce_desc* desc, const sce_buffers* buffers, sce_plan**
   p->sms = sms;
   p->device = dev;
   p->xm = desc->x_per_model ? desc->n_models : 1;
+  p->arith = resolve_arith(*desc);
   // CTA pairs by default for all four GEMMs (same-box A/B in profiles/r01g_pair_tuning.txt: -10 % encode,
   // -9 % decode, -3 % dcode, -21 % weight gradient on that box; env SCE_TUNE_PAIR_* = 0 switches one back)
   p->pair_encode = tune_flag("SCE_TUNE_PAIR_ENCODE", 1);
@@ -639,14 +771,11 @@ int sce_prepare(sce_plan* p, void* stream) {
   AdamHyper h = hyper_for(p, 1);
   int rc;
   if (d.variant == SCE_UNTIED) {
-    rc = launch_dict_rows<MODE_PREPARE>(p->b.encoder, nullptr, nullptr, nullptr, p->wenc_hi, p->wenc_lo, nullptr, rows,
-                                        d.d, 0, 0.f, h, st);
+    rc = launch_dict_rows<MODE_PREPARE>(p, 0, p->b.encoder, nullptr, nullptr, nullptr, nullptr, rows, d.d, 0, 0.f, h, st);
     if (rc) return rc;
-    rc = launch_dict_rows<MODE_PREPARE>(p->b.decoder, nullptr, nullptr, nullptr, p->wdec_hi, p->wdec_lo, nullptr, rows,
-                                        d.d, 1, d.norm_floor, h, st);
+    rc = launch_dict_rows<MODE_PREPARE>(p, 1, p->b.decoder, nullptr, nullptr, nullptr, nullptr, rows, d.d, 1, d.norm_floor, h, st);
   } else {
-    rc = launch_dict_rows<MODE_PREPARE>(p->b.encoder, nullptr, nullptr, nullptr, p->wenc_hi, p->wenc_lo, nullptr, rows,
-                                        d.d, 1, d.norm_floor, h, st);
+    rc = launch_dict_rows<MODE_PREPARE>(p, 0, p->b.encoder, nullptr, nullptr, nullptr, nullptr, rows, d.d, 1, d.norm_floor, h, st);
   }
   return rc;
 }
@@ -666,16 +795,16 @@ static int step_launches(sce_plan* p, const float* x, int B, float* out_losses, 
   const AdamHyper h = hyper_for(p, t);
   int launches = p->last_launches;
   if (d.variant == SCE_UNTIED) {
-    rc = launch_dict_rows<MODE_ADAM>(p->b.encoder, p->dw_enc, p->b.encoder_m, p->b.encoder_v, p->wenc_hi, p->wenc_lo,
-                                     nullptr, rows, d.d, 0, 0.f, h, st);
+    rc = launch_dict_rows<MODE_ADAM>(p, 0, p->b.encoder, p->dw_enc, p->b.encoder_m, p->b.encoder_v, nullptr, rows, d.d, 0,
+                                     0.f, h, st);
     if (rc) return rc;
-    rc = launch_dict_rows<MODE_ADAM>(p->b.decoder, p->dw_dec, p->b.decoder_m, p->b.decoder_v, p->wdec_hi, p->wdec_lo,
-                                     nullptr, rows, d.d, 1, d.norm_floor, h, st);
+    rc = launch_dict_rows<MODE_ADAM>(p, 1, p->b.decoder, p->dw_dec, p->b.decoder_m, p->b.decoder_v, nullptr, rows, d.d, 1,
+                                     d.norm_floor, h, st);
     if (rc) return rc;
     launches += 2;
   } else {
-    rc = launch_dict_rows<MODE_ADAM>(p->b.encoder, p->dw_enc, p->b.encoder_m, p->b.encoder_v, p->wenc_hi, p->wenc_lo,
-                                     nullptr, rows, d.d, 1, d.norm_floor, h, st);
+    rc = launch_dict_rows<MODE_ADAM>(p, 0, p->b.encoder, p->dw_enc, p->b.encoder_m, p->b.encoder_v, nullptr, rows, d.d, 1,
+                                     d.norm_floor, h, st);
     if (rc) return rc;
     ++launches;
   }
@@ -684,7 +813,7 @@ static int step_launches(sce_plan* p, const float* x, int B, float* out_losses, 
     const int n_part = ((B + kBM - 1) / kBM) * 4;
     bias_kernel<MODE_ADAM><<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(
         p->b.encoder_bias, p->b.bias_m, p->b.bias_v, p->db_part, n_part, d.n, d.n_models, p->b.bias_decay, p->bnorm,
-        nullptr, h);
+        nullptr, h, grad_out_scale(p, B));
     CUDA_TRY(cudaGetLastError());
     ++launches;
   }
@@ -771,25 +900,25 @@ int sce_grads(sce_plan* p, const float* x, int B, float* d_encoder, float* d_bia
   const AdamHyper h = hyper_for(p, 1);
   if (d.variant == SCE_UNTIED) {
     if (d_encoder) {
-      rc = launch_dict_rows<MODE_GRAD>(p->b.encoder, p->dw_enc, nullptr, nullptr, nullptr, nullptr, d_encoder, rows, d.d,
-                                       0, 0.f, h, st);
+      rc = launch_dict_rows<MODE_GRAD>(p, 0, p->b.encoder, p->dw_enc, nullptr, nullptr, d_encoder, rows, d.d, 0, 0.f, h, st);
       if (rc) return rc;
     }
     if (d_decoder) {
-      rc = launch_dict_rows<MODE_GRAD>(p->b.decoder, p->dw_dec, nullptr, nullptr, nullptr, nullptr, d_decoder, rows, d.d,
-                                       1, d.norm_floor, h, st);
+      rc = launch_dict_rows<MODE_GRAD>(p, 1, p->b.decoder, p->dw_dec, nullptr, nullptr, d_decoder, rows, d.d, 1, d.norm_floor,
+                                       h, st);
       if (rc) return rc;
     }
   } else if (d_encoder) {
-    rc = launch_dict_rows<MODE_GRAD>(p->b.encoder, p->dw_enc, nullptr, nullptr, nullptr, nullptr, d_encoder, rows, d.d, 1,
-                                     d.norm_floor, h, st);
+    rc = launch_dict_rows<MODE_GRAD>(p, 0, p->b.encoder, p->dw_enc, nullptr, nullptr, d_encoder, rows, d.d, 1, d.norm_floor, h,
+                                     st);
     if (rc) return rc;
   }
   if (p->b.encoder_bias && d_bias) {
     const long long tot = (long long)d.n_models * d.n;
     const int n_part = ((B + kBM - 1) / kBM) * 4;
     bias_kernel<MODE_GRAD><<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(
-        p->b.encoder_bias, nullptr, nullptr, p->db_part, n_part, d.n, d.n_models, p->b.bias_decay, p->bnorm, d_bias, h);
+        p->b.encoder_bias, nullptr, nullptr, p->db_part, n_part, d.n, d.n_models, p->b.bias_decay, p->bnorm, d_bias, h,
+        grad_out_scale(p, B));
     CUDA_TRY(cudaGetLastError());
   }
   return SCE_OK;
@@ -821,7 +950,10 @@ int sce_read_code(sce_plan* p, int B, float* out_code, void* stream) {
   const long long per = (long long)B * p->d.n;
   for (int m = 0; m < p->d.n_models; ++m) {
     const long long src = (long long)m * p->d.batch_max * p->d.n;
-    join_code_kernel<<<1024, 256, 0, st>>>(p->c_hi + src, p->c_lo + src, out_code + (long long)m * per, per / 2);
+    if (p->arith == kArithF16F8)
+      join_code_kernel<kArithF16F8><<<1024, 256, 0, st>>>(p->c_hi + src, nullptr, p->c_x8 + src, out_code + (long long)m * per, per / 2);
+    else
+      join_code_kernel<kArithBf16x3><<<1024, 256, 0, st>>>(p->c_hi + src, p->c_lo + src, nullptr, out_code + (long long)m * per, per / 2);
   }
   CUDA_TRY(cudaGetLastError());
   return SCE_OK;
@@ -841,6 +973,9 @@ int sce_gather_rows(const void* chunk, int chunk_is_half, long long n_rows, int 
 }
 
 int sce_last_launch_count(const sce_plan* plan) { return plan ? plan->last_launches : 0; }
+int sce_plan_arith(const sce_plan* plan) {
+  return !plan ? 0 : plan->arith == kArithF16F8 ? SCE_ARITH_F16F8 : SCE_ARITH_BF16X3;
+}
 
 int sce_profile_begin(sce_plan* p) {
   if (!p) return fail(SCE_ERR_INVALID, "plan is NULL");

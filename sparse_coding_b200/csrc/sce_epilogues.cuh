@@ -44,19 +44,36 @@ __device__ __forceinline__ void stage_row32(uint8_t* tile, int lane, const uint3
     *reinterpret_cast<uint4*>(tile + lane * 64 + ((q ^ sw) << 4)) =
         make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
 }
-// whole warp: wait until the previous tile pair has been read out, write the new one, launch its stores
+// 8-bit plane tile: 32 rows x 32 bytes, TMA 32-byte swizzle (16-byte chunk index ^= (row >> 2) & 1)
+__device__ __forceinline__ void stage_row32_u8(uint8_t* tile, int lane, const uint32_t* w /*[8]*/) {
+  const int sw = (lane >> 2) & 1;
+#pragma unroll
+  for (int q = 0; q < 2; ++q)
+    *reinterpret_cast<uint4*>(tile + lane * 32 + ((q ^ sw) << 4)) = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+}
+// whole warp: wait until the previous tiles have been read out, write the new ones, launch their stores.
+// bf16x3: whi / wx are the hi / lo planes. f16f8: whi is the fp16 plane, wx[0..7] the value-e5m2 plane and
+// wx[8..15] the residual-e5m2 plane (maps m_lo / m_x8).
+template <int ARITH>
 __device__ __forceinline__ void stage_and_store(uint8_t* stage, int lane, const uint32_t (&whi)[16],
-                                                const uint32_t (&wlo)[16], const CUtensorMap* m_hi,
-                                                const CUtensorMap* m_lo, int col, int row0, int model) {
+                                                const uint32_t (&wx)[16], const CUtensorMap* m_hi,
+                                                const CUtensorMap* m_lo, const CUtensorMap* m_x8, int col, int row0,
+                                                int model) {
   if (lane == 0) tma_store_wait_read();
   __syncwarp();
   stage_row32(stage, lane, whi);
-  stage_row32(stage + 2048, lane, wlo);
+  if constexpr (ARITH == kArithF16F8) {
+    stage_row32_u8(stage + 2048, lane, &wx[0]);
+    stage_row32_u8(stage + 3072, lane, &wx[8]);
+  } else {
+    stage_row32(stage + 2048, lane, wx);
+  }
   fence_proxy_async_smem();
   __syncwarp();
   if (lane == 0) {
     tma_store_3d(m_hi, stage, col, row0, model);
     tma_store_3d(m_lo, stage + 2048, col, row0, model);
+    if constexpr (ARITH == kArithF16F8) tma_store_3d(m_x8, stage + 3072, col, row0, model);
     tma_store_commit();
   }
 }
@@ -73,16 +90,38 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t& hi2, uint32_t
   lo2 = *reinterpret_cast<const uint32_t*>(&l);
 }
 
+// Pair `i` (0..15, compile-time after unrolling; pairs are produced in increasing order) of a 32-column chunk into
+// the packed plane words the stores take.
+template <int ARITH>
+__device__ __forceinline__ void split_pair(float a, float b, int i, uint32_t (&whi)[16], uint32_t (&wx)[16]) {
+  if constexpr (ARITH == kArithF16F8) {
+    uint32_t h8, l8;
+    split2_f16f8(a, b, whi[i], h8, l8);
+    if (i & 1) {
+      wx[i >> 1] |= h8 << 16;
+      wx[8 + (i >> 1)] |= l8 << 16;
+    } else {
+      wx[i >> 1] = h8;
+      wx[8 + (i >> 1)] = l8;
+    }
+  } else {
+    split2(a, b, whi[i], wx[i]);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // encode:  c = relu(acc + bias) -> (c_hi, c_lo);  per-tile partial sums of |c| and count(c > 0)
 // A score of exactly 0 is recorded as c_hi = -0.0 so that the backward pass can reproduce
 // clamp(min=0)'s gradient of 1 at z == 0 without keeping z.
 // ------------------------------------------------------------------------------------------------
-struct EpiEncode {
+// f16f8: a positive score below the smallest fp16 subnormal would round to +0 and read as "inactive" in the
+// backward pass; it is stored as the smallest subnormal instead (the residual plane carries the difference).
+template <int ARITH>
+struct EpiEncodeT {
   static constexpr int kCols = 32;
   static constexpr int kWarpStageBytes = 4096;
   struct Params {
-    CUtensorMap out_hi, out_lo;    // store maps of c_hi / c_lo: [M][B][n], box 32 x 32
+    CUtensorMap out_hi, out_lo, out_x8;  // store maps of the code planes: [M][B][n], box 32 x 32
     const float* bias;             // [M, n] or nullptr
     const unsigned char* mask;     // [M, n] (1 = coefficient unused) or nullptr
     float* part;                   // [M][tiles_m*8][tiles_n][2]  (sum c, nnz)
@@ -95,7 +134,7 @@ struct EpiEncode {
   uint8_t* stage;
   float l1 = 0.f;
   int nnz = 0;
-  __device__ EpiEncode(const Params& p, const TileCoord& t, int m, int n, uint8_t* st)
+  __device__ EpiEncodeT(const Params& p, const TileCoord& t, int m, int n, uint8_t* st)
       : P(p), T(t), m_total(m), n_total(n), stage(st) {}
 
   __device__ __forceinline__ void chunk(int c, const uint32_t (&r)[32]) {
@@ -117,16 +156,18 @@ struct EpiEncode {
           const float z0 = __uint_as_float(r[j + u]) + bb[u], z1 = __uint_as_float(r[j + u + 1]) + bb[u + 1];
           const bool p0 = z0 > 0.f, p1 = z1 > 0.f;
           const float c0 = p0 ? z0 : 0.f, c1 = p1 ? z1 : 0.f;
-          uint32_t h2, l2;
-          split2(c0, c1, h2, l2);
+          split_pair<ARITH>(c0, c1, (j + u) >> 1, whi, wlo);
+          uint32_t& h2 = whi[(j + u) >> 1];
+          if constexpr (ARITH == kArithF16F8) {
+            if (p0 && (h2 & 0xFFFFu) == 0u) h2 |= 0x00000001u;
+            if (p1 && (h2 >> 16) == 0u) h2 |= 0x00010000u;
+          }
           if (P.flag_zero) {
             if (z0 == 0.f) h2 |= 0x00008000u;
             if (z1 == 0.f) h2 |= 0x80000000u;
           }
           ls += c0 + c1;
           cnt += int(p0) + int(p1);
-          whi[(j + u) >> 1] = h2;
-          wlo[(j + u) >> 1] = l2;
         }
       }
     } else {
@@ -145,19 +186,22 @@ struct EpiEncode {
           ls += cv[u];
           cnt += cv[u] > 0.f ? 1 : 0;
         }
-        uint32_t h2, l2;
-        split2(cv[0], cv[1], h2, l2);
+        split_pair<ARITH>(cv[0], cv[1], j >> 1, whi, wlo);
+        uint32_t& h2 = whi[j >> 1];
+        if constexpr (ARITH == kArithF16F8) {
+          if (cv[0] > 0.f && (h2 & 0xFFFFu) == 0u) h2 |= 0x00000001u;
+          if (cv[1] > 0.f && (h2 >> 16) == 0u) h2 |= 0x00010000u;
+        }
         if (zf[0]) h2 |= 0x00008000u;
         if (zf[1]) h2 |= 0x80000000u;
-        whi[j >> 1] = h2;
-        wlo[j >> 1] = l2;
       }
     }
     if (row_ok) {
       l1 += ls;
       nnz += cnt;
     }
-    stage_and_store(stage, T.lane, whi, wlo, &P.out_hi, &P.out_lo, col, T.m_blk * kBM + T.warp_q * 32, T.model);
+    stage_and_store<ARITH>(stage, T.lane, whi, wlo, &P.out_hi, &P.out_lo, &P.out_x8, col,
+                           T.m_blk * kBM + T.warp_q * 32, T.model);
   }
   __device__ __forceinline__ void finish() {
     if (T.lane == 0) tma_store_wait_read();  // the staging tiles must outlive their bulk stores
@@ -172,23 +216,28 @@ struct EpiEncode {
 };
 
 // ------------------------------------------------------------------------------------------------
-// decode:  r = acc - x;  partial sum r^2;  g = r * 2/(B d) -> (g_hi, g_lo);  optional x^ store
+// decode:  r = acc - x;  partial sum r^2;  g = r * gscale -> planes of g;  optional x^ store
+// bf16x3: gscale = 2/(B d) (g is the loss gradient). f16f8: gscale = 1 — the fp16 plane could not hold 2r/(Bd)
+// (~1e-7), so the backward pass runs on the residual itself and its consumers carry the factor (dcode adds
+// alpha d/2 instead of alpha/B; the weight- and bias-gradient outputs are multiplied by 2/(B d)).
 // ------------------------------------------------------------------------------------------------
-struct EpiDecode {
+template <int ARITH>
+struct EpiDecodeT {
   static constexpr int kCols = 32;
   static constexpr int kWarpStageBytes = 0;
   struct Params {
     const float* x;                // [B, d] (x_model_stride = 0) or [M, B, d]
     long long x_model_stride;
-    __nv_bfloat16* g_hi;           // [M, B, d]
-    __nv_bfloat16* g_lo;
+    uint16_t* g_hi;                // [M, B, d] 16-bit plane
+    uint8_t* g_lo;                 // bf16x3: lo plane (2 B / element); f16f8: value-e5m2 plane
+    uint8_t* g_x8;                 // f16f8: residual-e5m2 plane
     float* x_hat;                  // optional [M, B, d] fp32 (evaluation / parity tests)
     float* part;                   // [M][tiles_m*8][tiles_n]  (sum r^2)
     long long g_model_stride;      // batch_max*d (workspace pitch)
     long long xhat_model_stride;   // B*d (caller's tensor)
     int ld;                        // d
     int tiles_m, tiles_n;
-    float gscale;                  // 2 / (B * d)
+    float gscale;                  // 2 / (B * d), or 1 (f16f8)
   };
   const Params& P;
   const TileCoord& T;
@@ -205,7 +254,7 @@ struct EpiDecode {
       xn[j] = (row_ok && col + 4 * j < n_total) ? __ldg(reinterpret_cast<const float4*>(x + 4 * j))
                                                : make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  __device__ EpiDecode(const Params& p, const TileCoord& t, int m, int n, uint8_t*) : P(p), T(t), m_total(m), n_total(n) {
+  __device__ EpiDecodeT(const Params& p, const TileCoord& t, int m, int n, uint8_t*) : P(p), T(t), m_total(m), n_total(n) {
     fetch_x(T.grp * 32);
   }
 
@@ -225,15 +274,24 @@ struct EpiDecode {
       const float r0 = ok ? __uint_as_float(r[j]) - xv.x : 0.f, r1 = ok ? __uint_as_float(r[j + 1]) - xv.y : 0.f;
       const float r2 = ok ? __uint_as_float(r[j + 2]) - xv.z : 0.f, r3 = ok ? __uint_as_float(r[j + 3]) - xv.w : 0.f;
       sq += r0 * r0 + r1 * r1 + r2 * r2 + r3 * r3;
-      split2(r0 * P.gscale, r1 * P.gscale, whi[j >> 1], wlo[j >> 1]);
-      split2(r2 * P.gscale, r3 * P.gscale, whi[(j >> 1) + 1], wlo[(j >> 1) + 1]);
+      split_pair<ARITH>(r0 * P.gscale, r1 * P.gscale, j >> 1, whi, wlo);
+      split_pair<ARITH>(r2 * P.gscale, r3 * P.gscale, (j >> 1) + 1, whi, wlo);
       if (P.x_hat && ok)
         *reinterpret_cast<float4*>(P.x_hat + (long long)T.model * P.xhat_model_stride + (long long)T.row * P.ld + col + j) =
             make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
                         __uint_as_float(r[j + 3]));
     }
-    store_bf16x32(P.g_hi + off, whi, n_total - col);
-    store_bf16x32(P.g_lo + off, wlo, n_total - col);
+    store_bf16x32(reinterpret_cast<__nv_bfloat16*>(P.g_hi) + off, whi, n_total - col);
+    if constexpr (ARITH == kArithF16F8) {
+#pragma unroll
+      for (int q = 0; q < 2; ++q)
+        if (q * 16 < n_total - col) {  // d % 16 == 0 in this arithmetic
+          *reinterpret_cast<uint4*>(P.g_lo + off + q * 16) = make_uint4(wlo[4 * q], wlo[4 * q + 1], wlo[4 * q + 2], wlo[4 * q + 3]);
+          *reinterpret_cast<uint4*>(P.g_x8 + off + q * 16) = make_uint4(wlo[8 + 4 * q], wlo[9 + 4 * q], wlo[10 + 4 * q], wlo[11 + 4 * q]);
+        }
+    } else {
+      store_bf16x32(reinterpret_cast<__nv_bfloat16*>(P.g_lo) + off, wlo, n_total - col);
+    }
   }
   __device__ __forceinline__ void finish() {
     const float a = warp_sum(sq);
@@ -246,13 +304,14 @@ struct EpiDecode {
 // dcode:  dz = (acc + (alpha/B) [c > 0]) * [z >= 0]  -> (dz_hi, dz_lo);
 //         per-warp column sums of dz (32 rows) -> bias-gradient partials
 // ------------------------------------------------------------------------------------------------
-struct EpiDcode {
+template <int ARITH>
+struct EpiDcodeT {
   static constexpr int kCols = 32;
   static constexpr int kWarpStageBytes = 4096;
   struct Params {
-    CUtensorMap out_hi, out_lo;    // store maps of dz_hi / dz_lo: [M][B][n], box 32 x 32
-    const __nv_bfloat16* c_hi;     // [M, B, n]
-    const float* l1_over_b;        // [M]: alpha_m / B
+    CUtensorMap out_hi, out_lo, out_x8;  // store maps of the dz planes: [M][B][n], box 32 x 32
+    const __nv_bfloat16* c_hi;     // [M, B, n] 16-bit plane of the code (bf16 or fp16: only sign / zero-ness is read)
+    const float* l1_over_b;        // [M]: alpha_m / B (f16f8: alpha_m d / 2, see EpiDecodeT)
     float* db_part;                // [M][tiles_m*4][n] or nullptr (no bias)
     long long c_model_stride;      // batch_max*n
     int ldc;                       // n
@@ -273,7 +332,7 @@ struct EpiDcode {
       cn[j] = (row_ok && col + j * 8 < n_total) ? __ldg(reinterpret_cast<const uint4*>(src + j * 8))
                                                 : make_uint4(0, 0, 0, 0);
   }
-  __device__ EpiDcode(const Params& p, const TileCoord& t, int m, int n, uint8_t* st)
+  __device__ EpiDcodeT(const Params& p, const TileCoord& t, int m, int n, uint8_t* st)
       : P(p), T(t), m_total(m), n_total(n), stage(st) {
     aB = __ldg(P.l1_over_b + T.model);
     fetch_c(T.grp * 32);
@@ -295,7 +354,7 @@ struct EpiDcode {
     uint32_t whi[16], wlo[16];
 #pragma unroll
     for (int j = 0; j < 32; j += 2) {
-      // bf16 bit patterns: 0x0001..0x7FFF positive (c > 0); 0x8000 is the "z == 0" flag written by encode
+      // bf16 / fp16 bit patterns: 0x0001..0x7FFF positive (c > 0); 0x8000 is the "z == 0" flag written by encode
       const uint32_t b0 = cw[j >> 1] & 0xFFFFu, b1 = cw[j >> 1] >> 16;
       const bool pos0 = (b0 - 1u) < 0x7FFFu, pos1 = (b1 - 1u) < 0x7FFFu;
       const bool gate0 = (b0 - 1u) < 0x8000u, gate1 = (b1 - 1u) < 0x8000u;
@@ -303,9 +362,10 @@ struct EpiDcode {
       const float v1 = gate1 ? __uint_as_float(r[j + 1]) + (pos1 ? aB : 0.f) : 0.f;
       dz[j] = v0;
       dz[j + 1] = v1;
-      split2(v0, v1, whi[j >> 1], wlo[j >> 1]);
+      split_pair<ARITH>(v0, v1, j >> 1, whi, wlo);
     }
-    stage_and_store(stage, T.lane, whi, wlo, &P.out_hi, &P.out_lo, col, T.m_blk * kBM + T.warp_q * 32, T.model);
+    stage_and_store<ARITH>(stage, T.lane, whi, wlo, &P.out_hi, &P.out_lo, &P.out_x8, col,
+                           T.m_blk * kBM + T.warp_q * 32, T.model);
     if (P.db_part && T.m_blk * kBM < m_total) {  // warp-uniform
       // transpose-reduce: 32 lanes x 32 columns -> lane j holds the sum of column j (31 shuffles)
 #pragma unroll
@@ -326,5 +386,9 @@ struct EpiDcode {
     if (T.lane == 0) tma_store_wait_read();
   }
 };
+
+using EpiEncode = EpiEncodeT<kArithBf16x3>;
+using EpiDecode = EpiDecodeT<kArithBf16x3>;
+using EpiDcode = EpiDcodeT<kArithBf16x3>;
 
 }  // namespace sce

@@ -38,22 +38,25 @@ struct TileCoord {
 
 template <class EpiParams>
 struct GemmParams {
+  // bf16x3: (hi, lo) bf16 planes. f16f8: hi = fp16 plane, lo = e5m2(x) plane, x8 = e5m2((x - fp16(x)) * 2^kLoShift) plane.
   CUtensorMap a_hi[kMaxSets], a_lo[kMaxSets], b_hi[kMaxSets], b_lo[kMaxSets];
+  CUtensorMap a_x8[kMaxSets], b_x8[kMaxSets];
   int a_batched[kMaxSets], b_batched[kMaxSets];  // 0: operand shared by all models
   int nsets;      // number of (A,B) operand pairs accumulated into the same tile
   int k_total;    // reduction length of each pair
-  int passes;     // 3: hi*hi + hi*lo + lo*hi, 1: hi*hi
+  int passes;     // 3: hi*hi + hi*lo + lo*hi (f16f8: fp16 hh + two fp8 cross terms), 1: hi*hi
   int n_models, m_total, n_total;
   int tiles_m, tiles_n;
   EpiParams epi;
 };
 
-template <int BN, int BK, bool A_MN, bool B_MN, int STAGES, int EPI_WARP_BYTES = 0, bool CTA2 = false>
+template <int BN, int BK, bool A_MN, bool B_MN, int STAGES, int EPI_WARP_BYTES = 0, bool CTA2 = false, int ARITH = 0>
 struct GemmSmem {
   static constexpr int kATile = kBM * BK * 2;   // bytes, one of hi/lo
   static constexpr int kBRows = CTA2 ? BN / 2 : BN;  // a CTA pair splits the B tile between its two CTAs
   static constexpr int kBTile = kBRows * BK * 2;
-  static constexpr int kStage = 2 * kATile + 2 * kBTile;
+  // bf16x3: hi and lo planes of A and B. f16f8: either the fp16 planes or the four 8-bit planes (same bytes).
+  static constexpr int kStage = ARITH == 1 ? kATile + kBTile : 2 * kATile + 2 * kBTile;
   static constexpr int kBarOff = STAGES * kStage;
   static constexpr int kEpiOff = kBarOff + 1024;  // barriers + tmem ptr live in the 1 KB before (keeps 1 KB alignment)
   static constexpr int kBytes = kEpiOff + kEpiWarps * EPI_WARP_BYTES + 1024 /*align slack*/;
@@ -74,14 +77,26 @@ struct GemmSmem {
 // keeps 128 accumulator rows in its own TMEM, loads its own 128 rows of A and HALF of the B tile, so a stage
 // is 1/3 smaller (three K=64 stages fit instead of two) and each SM reads a third less shared memory per
 // MMA. `tiles_m` then counts 256-row tiles; TileCoord::m_blk stays in 128-row units (2*tile_m + cta rank).
-template <class Epi, int BN, int BK, bool A_MN, bool B_MN, int STAGES, bool SPLIT_ACC = false, bool CTA2 = false>
+//
+// ARITH = kArithF16F8 (see sce_ptx.cuh, "fp16 + fp8 arithmetic"): a tile makes TWO sweeps over K. Sweep 1 streams the
+// 8-bit planes (a stage holds A.h8, A.l8, B.h8, B.l8 — the same bytes as A.f16 + B.f16) and issues the cross terms
+// as kind::f8f6f4; sweep 2 streams the fp16 planes and issues hh as kind::f16, its first instruction rescaling the
+// accumulator by 2^-kLoShift. One accumulator, so the double-buffered TMEM stages stay, and the chain of dominant
+// products is as short as with SPLIT_ACC.
+constexpr int kArithBf16x3 = 0, kArithF16F8 = 1;
+
+template <class Epi, int BN, int BK, bool A_MN, bool B_MN, int STAGES, bool SPLIT_ACC = false, bool CTA2 = false,
+          int ARITH = kArithBf16x3>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_split_kernel(const __grid_constant__ GemmParams<typename Epi::Params> p) {
+  constexpr bool F8 = ARITH == kArithF16F8;
+  static_assert(!F8 || !SPLIT_ACC, "f16f8 rescales in the accumulator; no split accumulators");
+  static_assert(!F8 || BK % 32 == 0, "an fp8 instruction covers K = 32");
   static_assert(BN % 64 == 0 && BN <= 256, "BN must be a multiple of 64, at most 256");
   static_assert(BK % 16 == 0 && BK <= 64, "BK in {16,32,48,64}");
   static_assert(A_MN || BK == 64 || BK == 32, "K-major A: one swizzled row per tile row, 128 B (BK=64) or 64 B (BK=32)");
   static_assert(B_MN || BK == 64 || BK == 32, "K-major B: one swizzled row per tile row, 128 B (BK=64) or 64 B (BK=32)");
-  using SM = GemmSmem<BN, BK, A_MN, B_MN, STAGES, Epi::kWarpStageBytes, CTA2>;
+  using SM = GemmSmem<BN, BK, A_MN, B_MN, STAGES, Epi::kWarpStageBytes, CTA2, ARITH>;
   static_assert(!CTA2 || BN % 128 == 0, "a CTA pair splits B in halves of whole 64-column boxes");
   constexpr int EC = Epi::kCols;  // accumulator columns handed to the epilogue per call (32 or 64)
   static_assert(EC == 32 || EC == 64, "epilogue chunk is 32 or 64 columns");
@@ -115,6 +130,10 @@ gemm_split_kernel(const __grid_constant__ GemmParams<typename Epi::Params> p) {
       if (three) {
         tma_prefetch_desc(&p.a_lo[s]);
         tma_prefetch_desc(&p.b_lo[s]);
+        if constexpr (F8) {
+          tma_prefetch_desc(&p.a_x8[s]);
+          tma_prefetch_desc(&p.b_x8[s]);
+        }
       }
     }
   }
@@ -147,7 +166,7 @@ gemm_split_kernel(const __grid_constant__ GemmParams<typename Epi::Params> p) {
   if (warp == 0) {
     // ======================= TMA producer =======================
     if (lane == 0) {
-      const uint32_t stage_bytes = three ? uint32_t(SM::kStage) : uint32_t(SM::kATile + SM::kBTile);
+      const uint32_t stage_bytes = (three && !F8) ? uint32_t(SM::kStage) : uint32_t(SM::kATile + SM::kBTile);
       // one copy: same-CTA barrier, or (pair) the cta_group::2 form that completes on CTA 0's barrier
       auto load = [&](void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
         if constexpr (CTA2) tma_load_3d_2cta(dst, m, bar, c0, c1, c2);
@@ -162,6 +181,64 @@ gemm_split_kernel(const __grid_constant__ GemmParams<typename Epi::Params> p) {
         const int m_blk = (rem / p.tiles_n) * (CTA2 ? 2 : 1) + cta_rank;
         const int n_blk = rem % p.tiles_n;
         const int b_row0 = n_blk * BN + cta_rank * kBHalf;
+        if constexpr (F8) {
+          // sweep 1: the 8-bit planes (skipped for passes == 1); sweep 2: the fp16 planes
+          for (int sweep = three ? 0 : 1; sweep < 2; ++sweep)
+            for (int set = 0; set < p.nsets; ++set) {
+              const int am = p.a_batched[set] ? model : 0;
+              const int bm = p.b_batched[set] ? model : 0;
+              for (int kb = 0; kb < kblocks; ++kb) {
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                uint8_t* st = smem + stage * SM::kStage;
+                if (!CTA2 || cta_rank == 0) mbar_expect_tx(&full_bar[stage], CTA2 ? 2 * stage_bytes : stage_bytes);
+                const int k0 = kb * BK;
+                if (sweep == 1) {
+                  uint8_t* sa = st;
+                  uint8_t* sb = st + SM::kATile;
+                  if constexpr (!A_MN) load(sa, &p.a_hi[set], &full_bar[stage], k0, m_blk * kBM, am);
+                  else {
+#pragma unroll
+                    for (int j = 0; j < kBM / 64; ++j)
+                      load(sa + j * (BK * 128), &p.a_hi[set], &full_bar[stage], m_blk * kBM + j * 64, k0, am);
+                  }
+                  if constexpr (!B_MN) load(sb, &p.b_hi[set], &full_bar[stage], k0, b_row0, bm);
+                  else {
+#pragma unroll
+                    for (int j = 0; j < kBHalf / 64; ++j)
+                      load(sb + j * (BK * 128), &p.b_hi[set], &full_bar[stage], b_row0 + j * 64, k0, bm);
+                  }
+                } else {
+                  uint8_t* sa_h = st;
+                  uint8_t* sa_l = st + SM::kATile / 2;
+                  uint8_t* sb_h = st + SM::kATile;
+                  uint8_t* sb_l = sb_h + SM::kBTile / 2;
+                  if constexpr (!A_MN) {
+                    load(sa_h, &p.a_lo[set], &full_bar[stage], k0, m_blk * kBM, am);
+                    load(sa_l, &p.a_x8[set], &full_bar[stage], k0, m_blk * kBM, am);
+                  } else {
+                    static_assert(!F8 || !A_MN || kBM == 128, "one 128-element box per MN-major 8-bit A tile");
+                    load(sa_h, &p.a_lo[set], &full_bar[stage], m_blk * kBM, k0, am);
+                    load(sa_l, &p.a_x8[set], &full_bar[stage], m_blk * kBM, k0, am);
+                  }
+                  if constexpr (!B_MN) {
+                    load(sb_h, &p.b_lo[set], &full_bar[stage], k0, b_row0, bm);
+                    load(sb_l, &p.b_x8[set], &full_bar[stage], k0, b_row0, bm);
+                  } else {
+                    static_assert(!F8 || !B_MN || kBHalf % 128 == 0, "MN-major 8-bit B tiles come in 128-element boxes");
+#pragma unroll
+                    for (int j = 0; j < kBHalf / 128; ++j) {
+                      load(sb_h + j * (BK * 128), &p.b_lo[set], &full_bar[stage], b_row0 + j * 128, k0, bm);
+                      load(sb_l + j * (BK * 128), &p.b_x8[set], &full_bar[stage], b_row0 + j * 128, k0, bm);
+                    }
+                  }
+                }
+                if (++stage == STAGES) {
+                  stage = 0;
+                  phase ^= 1;
+                }
+              }
+            }
+        } else {
         for (int set = 0; set < p.nsets; ++set) {
           const int am = p.a_batched[set] ? model : 0;
           const int bm = p.b_batched[set] ? model : 0;
@@ -200,6 +277,7 @@ gemm_split_kernel(const __grid_constant__ GemmParams<typename Epi::Params> p) {
             }
           }
         }
+        }
       }
     }
   } else if (warp == 1) {
@@ -209,6 +287,10 @@ gemm_split_kernel(const __grid_constant__ GemmParams<typename Epi::Params> p) {
       auto mma = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t acc_flag) {
         if constexpr (CTA2) umma_bf16_2cta(d, a, b, idesc, acc_flag);
         else umma_bf16(d, a, b, idesc, acc_flag);
+      };
+      auto mma16 = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t id, uint32_t acc_flag) {
+        if constexpr (CTA2) umma_bf16_2cta(d, a, b, id, acc_flag);
+        else umma_bf16(d, a, b, id, acc_flag);
       };
       auto commit = [&](uint64_t* bar) {
         if constexpr (CTA2) umma_commit_2cta(bar);
@@ -231,6 +313,65 @@ gemm_split_kernel(const __grid_constant__ GemmParams<typename Epi::Params> p) {
         const uint32_t d_tmem = tmem_base + uint32_t(acc * BN);
         const uint32_t d_cross = SPLIT_ACC ? tmem_base + uint32_t(BN) : d_tmem;
         uint32_t accumulate = 0;
+        if constexpr (F8) {
+          constexpr uint32_t i16 = make_idesc_fmt(CTA2 ? 2 * kBM : kBM, BN, A_MN, B_MN, 0, 0);  // f16 x f16
+          constexpr uint32_t i8 = make_idesc_fmt(CTA2 ? 2 * kBM : kBM, BN, A_MN, B_MN, 1, 1);   // e5m2 x e5m2
+          // 8-bit planes: K-major rows are BK bytes (64-byte or 32-byte swizzle); MN-major rows hold 128 elements
+          constexpr uint32_t a8_sbo = A_MN ? 1024 : (BK == 64 ? 512 : 256), a8_lt = A_MN ? 2 : (BK == 64 ? 4 : 6);
+          constexpr uint32_t b8_sbo = B_MN ? 1024 : (BK == 64 ? 512 : 256), b8_lt = B_MN ? 2 : (BK == 64 ? 4 : 6);
+          constexpr uint32_t a8_kstep = A_MN ? 4096 : 32, b8_kstep = B_MN ? 4096 : 32;  // bytes per K = 32 slice
+          const int iters = p.nsets * kblocks;
+          if (three) {
+            for (int it = 0; it < iters; ++it) {
+              mbar_wait(&full_bar[stage], phase);
+              tc_fence_after();
+              const uint32_t sa_h = smem_u32(smem + stage * SM::kStage);
+              const uint32_t sa_l = sa_h + SM::kATile / 2;
+              const uint32_t sb_h = sa_h + SM::kATile;
+              const uint32_t sb_l = sb_h + SM::kBTile / 2;
+#pragma unroll
+              for (int k = 0; k < BK / 32; ++k) {
+                const uint64_t ah = make_sdesc(sa_h + k * a8_kstep, a_lbo, a8_sbo, a8_lt);
+                const uint64_t al = make_sdesc(sa_l + k * a8_kstep, a_lbo, a8_sbo, a8_lt);
+                const uint64_t bh = make_sdesc(sb_h + k * b8_kstep, b_lbo, b8_sbo, b8_lt);
+                const uint64_t bl = make_sdesc(sb_l + k * b8_kstep, b_lbo, b8_sbo, b8_lt);
+                umma_f8<CTA2>(d_tmem, al, bh, i8, accumulate);
+                umma_f8<CTA2>(d_tmem, ah, bl, i8, 1);
+                accumulate = 1;
+              }
+              commit(&empty_bar[stage]);
+              if (++stage == STAGES) {
+                stage = 0;
+                phase ^= 1;
+              }
+            }
+          }
+          bool rescale = three;
+          for (int it = 0; it < iters; ++it) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + stage * SM::kStage);
+            const uint32_t sb = sa + SM::kATile;
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) {
+              const uint64_t ah = make_sdesc(sa + k * a_kstep, a_lbo, a_sbo, a_lt);
+              const uint64_t bh = make_sdesc(sb + k * b_kstep, b_lbo, b_sbo, b_lt);
+              if (k == 0 && rescale) {
+                umma_f16_rescale<CTA2>(d_tmem, ah, bh, i16);  // D = ah*bh + D * 2^-kLoShift
+                rescale = false;
+              } else {
+                mma16(d_tmem, ah, bh, i16, accumulate);
+              }
+              accumulate = 1;
+            }
+            commit(&empty_bar[stage]);
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+        if constexpr (!F8)
         for (int it = 0; it < p.nsets * kblocks; ++it) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
@@ -346,6 +487,7 @@ struct EpiStoreF32 {
     float* out;
     long long model_stride;  // elements
     int ld;                  // elements
+    float scale;             // out = acc * scale (0 is read as 1: zero-initialised params keep working)
   };
   const Params& P;
   const TileCoord& T;
@@ -355,11 +497,12 @@ struct EpiStoreF32 {
   __device__ __forceinline__ void chunk(int c, const uint32_t (&r)[32]) {
     if (T.row >= m_total) return;
     float* o = P.out + (long long)T.model * P.model_stride + (long long)T.row * P.ld + T.col0 + c;
+    const float sc = P.scale == 0.f ? 1.f : P.scale;
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
       if (T.col0 + c + j < n_total) {  // n_total % 4 == 0 is required by the host
-        float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
-                               __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+        float4 v = make_float4(__uint_as_float(r[j]) * sc, __uint_as_float(r[j + 1]) * sc,
+                               __uint_as_float(r[j + 2]) * sc, __uint_as_float(r[j + 3]) * sc);
         *reinterpret_cast<float4*>(o + j) = v;
       }
     }

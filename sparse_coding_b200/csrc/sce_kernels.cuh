@@ -4,25 +4,41 @@
 // Each is a single pass over its data with 16-byte accesses; algorithmic bytes per element are
 // listed in DESIGN.md.
 #pragma once
-#include "sce_ptx.cuh"
+#include "sce_gemm.cuh"
 
 namespace sce {
 
 // ------------------------------------------------------------------------------------------------
-// batch split: x fp32 [rows, d] -> (hi, lo) bf16
+// batch split: x fp32 [rows, d] -> operand planes. bf16x3: (hi, lo) bf16. f16f8: fp16 plane `hi`, value-e5m2
+// plane `lo` (1 B / element), residual-e5m2 plane `x8`.
 // ------------------------------------------------------------------------------------------------
-__global__ void split_rows_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi,
-                                  __nv_bfloat16* __restrict__ lo, long long n4) {
+// Four consecutive values -> the operand planes at element offset 4 * i4 (shared by every producer of operands).
+template <int ARITH>
+__device__ __forceinline__ void store_planes4(const float (&v)[4], void* hi, void* lo, void* x8, long long i4) {
+  if constexpr (ARITH == kArithF16F8) {
+    uint2 h16;
+    uint32_t h8, l8;
+    split4_f16f8(v, h16, h8, l8);
+    reinterpret_cast<uint2*>(hi)[i4] = h16;
+    reinterpret_cast<uint32_t*>(lo)[i4] = h8;
+    reinterpret_cast<uint32_t*>(x8)[i4] = l8;
+  } else {
+    __nv_bfloat16 h[4], l[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) split_bf16(v[u], h[u], l[u]);
+    reinterpret_cast<uint2*>(hi)[i4] = make_uint2(pack_bf16(h[0], h[1]), pack_bf16(h[2], h[3]));
+    reinterpret_cast<uint2*>(lo)[i4] = make_uint2(pack_bf16(l[0], l[1]), pack_bf16(l[2], l[3]));
+  }
+}
+
+template <int ARITH>
+__global__ void split_rows_kernel(const float* __restrict__ x, void* __restrict__ hi, void* __restrict__ lo,
+                                  void* __restrict__ x8, long long n4) {
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
     const float4 v = reinterpret_cast<const float4*>(x)[i];
-    __nv_bfloat16 h[4], l[4];
-    split_bf16(v.x, h[0], l[0]);
-    split_bf16(v.y, h[1], l[1]);
-    split_bf16(v.z, h[2], l[2]);
-    split_bf16(v.w, h[3], l[3]);
-    reinterpret_cast<uint2*>(hi)[i] = make_uint2(pack_bf16(h[0], h[1]), pack_bf16(h[2], h[3]));
-    reinterpret_cast<uint2*>(lo)[i] = make_uint2(pack_bf16(l[0], l[1]), pack_bf16(l[2], l[3]));
+    const float vv[4] = {v.x, v.y, v.z, v.w};
+    store_planes4<ARITH>(vv, hi, lo, x8, i);
   }
 }
 
@@ -114,13 +130,12 @@ __device__ __forceinline__ float adam_apply(float p, float g, float& m, float& v
 // ------------------------------------------------------------------------------------------------
 enum { MODE_PREPARE = 0, MODE_ADAM = 1, MODE_GRAD = 2 };
 
-template <int NV, int MODE>
+template <int NV, int MODE, int ARITH>
 __global__ void __launch_bounds__(128) dict_rows_kernel(float* __restrict__ e, const float* __restrict__ dw,
                                                         float* __restrict__ m, float* __restrict__ v,
-                                                        __nv_bfloat16* __restrict__ w_hi,
-                                                        __nv_bfloat16* __restrict__ w_lo,
-                                                        float* __restrict__ grad_out, int d, int normalize,
-                                                        float floor, AdamHyper h) {
+                                                        void* __restrict__ w_hi, void* __restrict__ w_lo,
+                                                        void* __restrict__ w_x8, float* __restrict__ grad_out, int d,
+                                                        int normalize, float floor, AdamHyper h) {
   __shared__ float red[8];
   const long long row = blockIdx.x;
   const long long base = row * d;
@@ -195,11 +210,7 @@ __global__ void __launch_bounds__(128) dict_rows_kernel(float* __restrict__ e, c
     const int c = (i * 128 + threadIdx.x) * 4;
     if (c < d) {
       const float w[4] = {ev[i].x / s, ev[i].y / s, ev[i].z / s, ev[i].w / s};
-      __nv_bfloat16 hh[4], ll[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) split_bf16(w[u], hh[u], ll[u]);
-      *reinterpret_cast<uint2*>(w_hi + base + c) = make_uint2(pack_bf16(hh[0], hh[1]), pack_bf16(hh[2], hh[3]));
-      *reinterpret_cast<uint2*>(w_lo + base + c) = make_uint2(pack_bf16(ll[0], ll[1]), pack_bf16(ll[2], ll[3]));
+      store_planes4<ARITH>(w, w_hi, w_lo, w_x8, (base + c) >> 2);
     }
   }
 }
@@ -231,7 +242,7 @@ template <int MODE>
 __global__ void bias_kernel(float* __restrict__ bias, float* __restrict__ m, float* __restrict__ v,
                             const float* __restrict__ db_part, int n_part, int n, int n_models,
                             const float* __restrict__ bias_decay, const float* __restrict__ bnorm,
-                            float* __restrict__ grad_out, AdamHyper h) {
+                            float* __restrict__ grad_out, AdamHyper h, float part_scale) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)n_models * n) return;
   const int model = int(i / n);
@@ -239,6 +250,7 @@ __global__ void bias_kernel(float* __restrict__ bias, float* __restrict__ m, flo
   const float* p = db_part + (long long)model * n_part * n + j;
   float g = 0.f;
   for (int k = 0; k < n_part; ++k) g += p[(long long)k * n];
+  g *= part_scale;  // f16f8: the partials are sums of dz * B d / 2 (see EpiDecodeT)
   const float b = bias[i];
   if (bias_decay) {
     const float bd = bias_decay[model], nb = bnorm[model];
@@ -311,15 +323,24 @@ __global__ void __launch_bounds__(256) finalize_kernel(const float* __restrict__
 // ------------------------------------------------------------------------------------------------
 // dense fp32 code from its (hi, lo) pair (the -0.0 "z == 0" flag decodes to +0)
 // ------------------------------------------------------------------------------------------------
-__global__ void join_code_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo,
+template <int ARITH>
+__global__ void join_code_kernel(const void* __restrict__ hi, const void* __restrict__ lo, const void* __restrict__ x8,
                                  float* __restrict__ out, long long n2) {
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += stride) {
-    const __nv_bfloat162 h = reinterpret_cast<const __nv_bfloat162*>(hi)[i];
-    const __nv_bfloat162 l = reinterpret_cast<const __nv_bfloat162*>(lo)[i];
     float2 o;
-    o.x = __low2float(h) + __low2float(l);
-    o.y = __high2float(h) + __high2float(l);
+    if constexpr (ARITH == kArithF16F8) {
+      const float2 h = __half22float2(reinterpret_cast<const __half2*>(hi)[i]);
+      const uint32_t l = reinterpret_cast<const uint16_t*>(x8)[i];
+      constexpr float kInv = 1.f / float(1 << kLoShift);
+      o.x = h.x + e5m2_to_float(l & 0xFFu) * kInv;
+      o.y = h.y + e5m2_to_float(l >> 8) * kInv;
+    } else {
+      const __nv_bfloat162 h = reinterpret_cast<const __nv_bfloat162*>(hi)[i];
+      const __nv_bfloat162 l = reinterpret_cast<const __nv_bfloat162*>(lo)[i];
+      o.x = __low2float(h) + __low2float(l);
+      o.y = __high2float(h) + __high2float(l);
+    }
     if (o.x == 0.f) o.x = 0.f;  // -0 -> +0
     if (o.y == 0.f) o.y = 0.f;
     reinterpret_cast<float2*>(out)[i] = o;
@@ -381,10 +402,11 @@ __device__ __forceinline__ float key2relu(uint32_t key) {  // relu(float behind 
 // Rows are processed four elements per thread (n % 8 == 0 is guaranteed by the plan) with UNROLL independent
 // 16-byte loads in flight per thread: the first version (one 4-byte load per iteration) was latency-bound at
 // 1.1 TB/s (profiles: long-scoreboard stall 9.2 per issue).
+template <int ARITH>
 __global__ void __launch_bounds__(256) topk_select_kernel(const float* __restrict__ scores,
                                                           const long long* __restrict__ sparsity,
-                                                          __nv_bfloat16* __restrict__ c_hi,
-                                                          __nv_bfloat16* __restrict__ c_lo,
+                                                          void* __restrict__ c_hi, void* __restrict__ c_lo,
+                                                          void* __restrict__ c_x8,
                                                           float* __restrict__ part /*[M][B][2]*/, int B, int n,
                                                           long long model_stride /*elements between models*/,
                                                           int use_cand /*0: rows too long for a candidate list in smem*/) {
@@ -485,23 +507,9 @@ __global__ void __launch_bounds__(256) topk_select_kernel(const float* __restric
   const uint32_t take_ties = sh_remaining; // number of elements == kth to keep
   const bool all_ties_kept = sh_neq == take_ties;
   float l1 = 0.f, cnt = 0.f;
-  uint2* out_hi = reinterpret_cast<uint2*>(c_hi + base);
-  uint2* out_lo = reinterpret_cast<uint2*>(c_lo + base);
   auto emit = [&](int i, float c0, float c1, float c2, float c3) {
-    uint32_t h01, l01, h23, l23;
-    {
-      __nv_bfloat16 h[4], l[4];
-      split_bf16(c0, h[0], l[0]);
-      split_bf16(c1, h[1], l[1]);
-      split_bf16(c2, h[2], l[2]);
-      split_bf16(c3, h[3], l[3]);
-      h01 = pack_bf16(h[0], h[1]);
-      h23 = pack_bf16(h[2], h[3]);
-      l01 = pack_bf16(l[0], l[1]);
-      l23 = pack_bf16(l[2], l[3]);
-    }
-    out_hi[i] = make_uint2(h01, h23);
-    out_lo[i] = make_uint2(l01, l23);
+    const float cv4[4] = {c0, c1, c2, c3};
+    store_planes4<ARITH>(cv4, c_hi, c_lo, c_x8, (base >> 2) + i);
     l1 += c0 + c1 + c2 + c3;
     cnt += (c0 > 0.f ? 1.f : 0.f) + (c1 > 0.f ? 1.f : 0.f) + (c2 > 0.f ? 1.f : 0.f) + (c3 > 0.f ? 1.f : 0.f);
   };

@@ -9,6 +9,8 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_fp8.h>
 
 namespace sce {
 
@@ -265,6 +267,53 @@ __device__ __forceinline__ void umma_commit_2cta(uint64_t* bar) {
 }
 
 // ----------------------------------------------------------------------------------------------
+// fp16 + fp8 arithmetic ("f16f8"): x ~= h + l with h = fp16(x) (11 significant bits) and l = x - h, |l| <= 2^-11 |x|.
+// The product a*b = ah*bh + (al*bh + ah*bl) + O(2^-22): the dominant term runs as kind::f16 on the fp16 planes,
+// the two cross terms need only ~3 significant bits and run as kind::f8f6f4 (E5M2 x E5M2, K = 32 per
+// instruction, twice the rate) on 8-bit planes: h8 = e5m2(x) and l8 = e5m2(l * 2^kLoShift). The cross terms are
+// accumulated FIRST (they carry the factor 2^kLoShift) and the first hh instruction of the tile rescales the
+// accumulator with tcgen05.mma's scale-input-d: D = A*B + D * 2^-kLoShift. Cost: 1 + 2 * 1/2 = 2 pass
+// equivalents instead of the 3 of the bf16 split, one accumulator.
+// ----------------------------------------------------------------------------------------------
+constexpr int kLoShift = 11;  // |l| * 2^11 <= |x|: the scaled residual has the range of x itself (fits E5M2 when x fits fp16)
+
+// Instruction descriptor with explicit operand formats. kind::f16: 0 = f16, 1 = bf16. kind::f8f6f4: 0 = e4m3, 1 = e5m2.
+__host__ __device__ constexpr uint32_t make_idesc_fmt(int M, int N, bool a_mn, bool b_mn, uint32_t afmt, uint32_t bfmt) {
+  return (1u << 4) | (afmt << 7) | (bfmt << 10) | (uint32_t(a_mn) << 15) | (uint32_t(b_mn) << 16) |
+         (uint32_t(N >> 3) << 17) | (uint32_t(M >> 4) << 24);
+}
+
+template <bool CTA2>
+__device__ __forceinline__ void umma_f8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if constexpr (CTA2) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+                 "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+                 : "memory");
+  } else {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+                 "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+                 : "memory");
+  }
+}
+// D = A*B + D * 2^-kLoShift (kind::f16 only; the scale is an immediate)
+template <bool CTA2>
+__device__ __forceinline__ void umma_f16_rescale(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
+  if constexpr (CTA2) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 1, 0;\n\t"
+                 "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p, %4;\n\t}\n" ::"r"(tmem_d),
+                 "l"(adesc), "l"(bdesc), "r"(idesc), "n"(kLoShift)
+                 : "memory");
+  } else {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 1, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p, %4;\n\t}\n" ::"r"(tmem_d),
+                 "l"(adesc), "l"(bdesc), "r"(idesc), "n"(kLoShift)
+                 : "memory");
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
 // bf16 hi/lo split: x ~= hi + lo with hi = bf16(x), lo = bf16(x - hi); |x - hi - lo| <= 2^-17 |x|.
 // ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
@@ -273,6 +322,28 @@ __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bflo
 }
 __device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat16 a, __nv_bfloat16 b) {
   return uint32_t(__bfloat16_as_ushort(a)) | (uint32_t(__bfloat16_as_ushort(b)) << 16);
+}
+
+// f16f8 planes of a pair of values: packed fp16x2 (low half = a), packed e5m2x2 of the values and of the scaled
+// residuals. Values beyond the fp16 range become inf in the fp16 plane (and NaN in the products): visible, not silent.
+__device__ __forceinline__ void split2_f16f8(float a, float b, uint32_t& h16x2, uint32_t& h8x2, uint32_t& l8x2) {
+  const __half2 h = __floats2half2_rn(a, b);
+  h16x2 = *reinterpret_cast<const uint32_t*>(&h);
+  const float2 hf = __half22float2(h);
+  constexpr float kS = float(1 << kLoShift);
+  l8x2 = __nv_cvt_float2_to_fp8x2(make_float2((a - hf.x) * kS, (b - hf.y) * kS), __NV_SATFINITE, __NV_E5M2);
+  h8x2 = __nv_cvt_float2_to_fp8x2(make_float2(a, b), __NV_SATFINITE, __NV_E5M2);
+}
+// four consecutive values -> 8 B of the fp16 plane, 4 B of each 8-bit plane
+__device__ __forceinline__ void split4_f16f8(const float (&v)[4], uint2& h16, uint32_t& h8, uint32_t& l8) {
+  uint32_t a8, al, b8, bl;
+  split2_f16f8(v[0], v[1], h16.x, a8, al);
+  split2_f16f8(v[2], v[3], h16.y, b8, bl);
+  h8 = a8 | (b8 << 16);
+  l8 = al | (bl << 16);
+}
+__device__ __forceinline__ float e5m2_to_float(uint32_t byte) {  // e5m2 is the high byte of an fp16
+  return __half2float(__ushort_as_half((unsigned short)(byte << 8)));
 }
 
 }  // namespace sce

@@ -58,4 +58,22 @@ inline bool make_tmap_bf16_store32(CUtensorMap* map, const void* base, uint64_t 
                             CU_TENSOR_MAP_SWIZZLE_64B);
 }
 
+// An 8-bit tensor (the e5m2 planes of the f16f8 arithmetic) seen as [models][rows][cols], boxes of
+// [1][box_rows][box_cols] bytes. K-major operand tiles: box_cols = BK with the 64-byte (BK = 64) or 32-byte
+// (BK = 32) swizzle; MN-major tiles: box_cols = 128 with the 128-byte swizzle; epilogue stores: 32 x 32, 32-byte swizzle.
+inline bool make_tmap_u8_box(CUtensorMap* map, const void* base, uint64_t models, uint64_t rows, uint64_t cols,
+                             uint64_t row_pitch_elems, uint64_t model_pitch_elems, uint32_t box_cols,
+                             uint32_t box_rows, CUtensorMapSwizzle swizzle) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[3] = {cols, rows, models};
+  cuuint64_t strides[2] = {row_pitch_elems, model_pitch_elems};
+  cuuint32_t box[3] = {box_cols, box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
 }  // namespace sce

@@ -142,13 +142,14 @@ class CodeProxy:
 class FunctionalEnsemble:
     def __init__(self, models, sig, optimizer_func, optimizer_kwargs, device=None, no_stacking=False,
                  adam_count_mode: str = "frozen_t1", fwd_passes: int = 3, bwd_passes: int = 3,
-                 materialize_code: bool = False):
+                 materialize_code: bool = False, arith: str = "auto"):
         """``models``: list of (params, buffers) from ``sig.init``; ``optimizer_func``: ``torchopt.adam`` (if
         installed), :func:`sparse_coding_b200.optim.adam`, or the string "adam"; ``optimizer_kwargs``: ``{"lr": …}``.
         ``no_stacking`` is accepted for API compatibility (the reference needs it for TopK because ``torch.topk``
         with a data-dependent k cannot be vmapped; the engine batches TopK models natively).
         Extra keywords (engine-only): ``adam_count_mode`` "frozen_t1" (reference behaviour) or
-        "standard"; ``fwd_passes`` / ``bwd_passes`` 3 (split-bf16, fp32-grade) or 1 (plain bf16)."""
+        "standard"; ``fwd_passes`` / ``bwd_passes`` 3 (split operands, fp32-grade) or 1 (16-bit plane only);
+        ``arith`` "auto" | "bf16x3" | "f16f8": how fp32 operands reach the tensor cores (include/sce.h, sce_arith)."""
         if device is None:
             first = next(iter(models[0][0].values()))
             self.device = first.device
@@ -165,6 +166,9 @@ class FunctionalEnsemble:
         self.optimizer = resolve_optimizer(optimizer_func, optimizer_kwargs)
         self.adam_count_mode = adam_count_mode
         self.fwd_passes, self.bwd_passes = fwd_passes, bwd_passes
+        if arith not in _lib.ARITH_CODE:
+            raise ValueError(f"arith must be one of {sorted(_lib.ARITH_CODE)}, got {arith!r}")
+        self.arith = arith
         self.materialize_code = materialize_code
         self.optim_states = {
             "mu": _tree_map(torch.zeros_like, self.params),
@@ -235,7 +239,8 @@ class FunctionalEnsemble:
             eps_root=cfg.eps_root,
             adam_count_mode=_lib.SCE_ADAM_FROZEN_T1 if self.adam_count_mode == "frozen_t1" else _lib.SCE_ADAM_STANDARD,
             fwd_passes=self.fwd_passes, bwd_passes=self.bwd_passes,
-            norm_floor=0.0 if self._variant == "topk" else 1e-8)
+            norm_floor=0.0 if self._variant == "topk" else 1e-8,
+            arith=_lib.ARITH_CODE[getattr(self, "arith", "auto")])
         nbytes = lib.sce_workspace_bytes(C.byref(desc))
         if nbytes == 0:
             _lib.check(-1, "sce_workspace_bytes")
@@ -415,6 +420,13 @@ class FunctionalEnsemble:
     def gpu_launches_last_call(self) -> int:
         return int(_lib.load().sce_last_launch_count(self._plan)) if self._plan is not None else 0
 
+    def resolved_arith(self):
+        """"bf16x3" or "f16f8": what the current plan runs (``arith="auto"`` resolves per shape); None before the
+        first step."""
+        if self._plan is None:
+            return None
+        return _lib.ARITH_NAME.get(int(_lib.load().sce_plan_arith(self._plan)))
+
     def unstack(self, device=None):
         params = unstack_dict(self.params, self.n_models, device=device)
         buffers = unstack_dict(self.buffers, self.n_models, device=device)
@@ -427,6 +439,7 @@ class FunctionalEnsemble:
             "sig": self.sig, "no_stacking": self.no_stacking, "optimizer_func": self.optimizer_func,
             "optimizer_kwargs": self.optimizer_kwargs, "optim_states": self.optim_states,
             "adam_count_mode": self.adam_count_mode, "fwd_passes": self.fwd_passes, "bwd_passes": self.bwd_passes,
+            "arith": getattr(self, "arith", "auto"),
             "materialize_code": self.materialize_code, "steps": self._steps,
         }
 
@@ -437,6 +450,7 @@ class FunctionalEnsemble:
                   "optimizer_kwargs", "optim_states"):
             setattr(self, k, state_dict[k])
         self.adam_count_mode = state_dict.get("adam_count_mode", "frozen_t1")
+        self.arith = state_dict.get("arith", "auto")
         self.fwd_passes = state_dict.get("fwd_passes", 3)
         self.bwd_passes = state_dict.get("bwd_passes", 3)
         self.materialize_code = state_dict.get("materialize_code", False)

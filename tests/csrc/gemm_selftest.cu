@@ -7,6 +7,9 @@
 #include <cstring>
 #include <vector>
 
+#include <cuda_fp16.h>
+#include <cuda_fp8.h>
+
 #include "../../sparse_coding_b200/csrc/sce_gemm.cuh"
 #include "../../sparse_coding_b200/csrc/sce_tmap.h"
 
@@ -93,7 +96,7 @@ static bool tmaps(const Operand& o, uint32_t box_rows_kmajor, int BK, CUtensorMa
 
 template <int BN, int BK, bool A_MN, bool B_MN, int STAGES, bool SPLIT = false, bool CTA2 = false>
 static bool run_case(const char* name, int models, int M, int N, int K, int nsets, int passes,
-                     bool a_shared, bool b_shared) {
+                     bool a_shared, bool b_shared, int reps = 1) {
   Operand A[2], B[2];
   for (int s = 0; s < nsets; ++s) {
     make_operand(A[s], a_shared ? 1 : models, M, K, A_MN);
@@ -139,8 +142,8 @@ static bool run_case(const char* name, int models, int M, int N, int K, int nset
   cudaEvent_t e0, e1;
   CK(cudaEventCreate(&e0));
   CK(cudaEventCreate(&e1));
-  CK(cudaEventRecord(e0));
-  {
+  for (int rep = 0; rep < reps + (reps > 1 ? 2 : 0); ++rep) {
+    if (rep == (reps > 1 ? 2 : 0)) CK(cudaEventRecord(e0));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(kGemmThreads);
@@ -163,6 +166,7 @@ static bool run_case(const char* name, int models, int M, int N, int K, int nset
   }
   float ms = 0;
   CK(cudaEventElapsedTime(&ms, e0, e1));
+  ms /= reps;
 
   std::vector<float> out(out_elems);
   CK(cudaMemcpy(out.data(), d_out, out_elems * 4, cudaMemcpyDeviceToHost));
@@ -239,14 +243,210 @@ static bool run_case(const char* name, int models, int M, int N, int K, int nset
   return ok;
 }
 
+// ------------------------------------------------------------------------------------------------
+// f16f8 arithmetic: fp16 plane + two e5m2 planes (value, scaled residual); see sce_ptx.cuh
+// ------------------------------------------------------------------------------------------------
+static float e5m2_to_float(uint8_t v) {
+  __half_raw hr = __nv_cvt_fp8_to_halfraw(v, __NV_E5M2);
+  return __half2float(__half(hr));
+}
+struct OperandF8 {
+  int models, rows, K;
+  bool mn;
+  std::vector<float> x;
+  std::vector<__half> h;
+  std::vector<uint8_t> h8, l8;
+  __half* d_h = nullptr;
+  uint8_t *d_h8 = nullptr, *d_l8 = nullptr;
+  int pitch;  // elements between consecutive rows (K-major) / k (MN-major): multiple of 16, TMA strides are 16-byte units
+  size_t idx(int m, int r, int k) const { return mn ? ((size_t)m * K + k) * pitch + r : ((size_t)m * rows + r) * pitch + k; }
+};
+static void make_operand_f8(OperandF8& o, int models, int rows, int K, bool mn, float scale) {
+  o.models = models; o.rows = rows; o.K = K; o.mn = mn;
+  o.pitch = ((mn ? rows : K) + 15) / 16 * 16;
+  size_t n = (size_t)models * (mn ? K : rows) * o.pitch;
+  o.x.resize(n); o.h.resize(n); o.h8.resize(n); o.l8.resize(n);
+  for (size_t i = 0; i < n; ++i) {
+    float v = frand() * scale;
+    o.x[i] = v;
+    o.h[i] = __float2half_rn(v);
+    o.h8[i] = __nv_cvt_float_to_fp8(v, __NV_SATFINITE, __NV_E5M2);
+    o.l8[i] = __nv_cvt_float_to_fp8((v - __half2float(o.h[i])) * float(1 << kLoShift), __NV_SATFINITE, __NV_E5M2);
+  }
+  CK(cudaMalloc(&o.d_h, n * 2)); CK(cudaMalloc(&o.d_h8, n)); CK(cudaMalloc(&o.d_l8, n));
+  CK(cudaMemcpy(o.d_h, o.h.data(), n * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(o.d_h8, o.h8.data(), n, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(o.d_l8, o.l8.data(), n, cudaMemcpyHostToDevice));
+}
+static bool tmaps_f8(const OperandF8& o, uint32_t box_rows_kmajor, int BK, CUtensorMap* h, CUtensorMap* h8, CUtensorMap* l8) {
+  const uint64_t mp = (uint64_t)(o.mn ? o.K : o.rows) * o.pitch;
+  if (!o.mn) {
+    const CUtensorMapSwizzle sw16 = BK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+    const CUtensorMapSwizzle sw8 = BK == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+    return make_tmap_bf16_box(h, o.d_h, o.models, o.rows, o.K, o.pitch, mp, BK, box_rows_kmajor, sw16) &&
+           make_tmap_u8_box(h8, o.d_h8, o.models, o.rows, o.K, o.pitch, mp, BK, box_rows_kmajor, sw8) &&
+           make_tmap_u8_box(l8, o.d_l8, o.models, o.rows, o.K, o.pitch, mp, BK, box_rows_kmajor, sw8);
+  }
+  return make_tmap_bf16(h, o.d_h, o.models, o.K, o.rows, o.pitch, mp, BK) &&
+         make_tmap_u8_box(h8, o.d_h8, o.models, o.K, o.rows, o.pitch, mp, 128, BK, CU_TENSOR_MAP_SWIZZLE_128B) &&
+         make_tmap_u8_box(l8, o.d_l8, o.models, o.K, o.rows, o.pitch, mp, 128, BK, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
+template <int BN, int BK, bool A_MN, bool B_MN, int STAGES, bool CTA2>
+static bool run_case_f8(const char* name, int models, int M, int N, int K, int nsets, int passes, bool a_shared,
+                        bool b_shared, int reps = 1) {
+  OperandF8 A[2], B[2];
+  for (int s = 0; s < nsets; ++s) {
+    make_operand_f8(A[s], a_shared ? 1 : models, M, K, A_MN, 3.0f);
+    make_operand_f8(B[s], b_shared ? 1 : models, N, K, B_MN, 0.25f);
+  }
+  float* d_out;
+  size_t out_elems = (size_t)models * M * N;
+  CK(cudaMalloc(&d_out, out_elems * 4));
+  CK(cudaMemset(d_out, 0xFF, out_elems * 4));
+  GemmParams<EpiStoreF32::Params> p;
+  memset(&p, 0, sizeof(p));
+  for (int s = 0; s < nsets; ++s) {
+    if (!tmaps_f8(A[s], kBM, BK, &p.a_hi[s], &p.a_lo[s], &p.a_x8[s]) ||
+        !tmaps_f8(B[s], CTA2 ? BN / 2 : BN, BK, &p.b_hi[s], &p.b_lo[s], &p.b_x8[s])) {
+      printf("[%s] tensor map encode failed\n", name);
+      return false;
+    }
+    p.a_batched[s] = a_shared ? 0 : 1;
+    p.b_batched[s] = b_shared ? 0 : 1;
+  }
+  p.nsets = nsets; p.k_total = K; p.passes = passes; p.n_models = models; p.m_total = M; p.n_total = N;
+  const int tile_rows = CTA2 ? 2 * kBM : kBM;
+  p.tiles_m = (M + tile_rows - 1) / tile_rows;
+  p.tiles_n = (N + BN - 1) / BN;
+  p.epi.out = d_out; p.epi.model_stride = (long long)M * N; p.epi.ld = N;
+  using SM = GemmSmem<BN, BK, A_MN, B_MN, STAGES, 0, CTA2, kArithF16F8>;
+  auto kern = gemm_split_kernel<EpiStoreF32, BN, BK, A_MN, B_MN, STAGES, false, CTA2, kArithF16F8>;
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kBytes));
+  int sms = 0;
+  CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
+  int tiles = models * p.tiles_m * p.tiles_n;
+  const int units = CTA2 ? sms / 2 : sms;
+  int grid = (tiles < units ? tiles : units) * (CTA2 ? 2 : 1);
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  float ms = 0;
+  for (int rep = 0; rep < reps + (reps > 1 ? 2 : 0); ++rep) {
+    if (rep == (reps > 1 ? 2 : 0)) CK(cudaEventRecord(e0));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kGemmThreads); cfg.dynamicSmemBytes = SM::kBytes; cfg.stream = 0;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CTA2 ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    CK(cudaLaunchKernelEx(&cfg, kern, p));
+  }
+  CK(cudaEventRecord(e1));
+  cudaError_t err = cudaDeviceSynchronize();
+  if (err != cudaSuccess) {
+    printf("[%s] kernel failed: %s\n", name, cudaGetErrorString(err));
+    exit(3);
+  }
+  CK(cudaEventElapsedTime(&ms, e0, e1));
+  ms /= reps;
+  std::vector<float> out(out_elems);
+  CK(cudaMemcpy(out.data(), d_out, out_elems * 4, cudaMemcpyDeviceToHost));
+  double max_err_exact = 0, max_ref = 0, se_full = 0, s_full = 0;
+  long long bad = 0;
+  int fb[3] = {-1, -1, -1};
+  int rstep = M > 512 ? 37 : 1, cstep = N > 512 ? 29 : 1;
+  const double inv = 1.0 / double(1 << kLoShift);
+  for (int m = 0; m < models; ++m)
+    for (int i = 0; i < M; i += rstep)
+      for (int j = 0; j < N; j += cstep) {
+        double hh = 0, cr = 0, fu = 0;
+        for (int s = 0; s < nsets; ++s) {
+          const int am = a_shared ? 0 : m, bm = b_shared ? 0 : m;
+          for (int k = 0; k < K; ++k) {
+            size_t ia = A[s].idx(am, i, k), ib = B[s].idx(bm, j, k);
+            hh += (double)__half2float(A[s].h[ia]) * (double)__half2float(B[s].h[ib]);
+            cr += (double)e5m2_to_float(A[s].l8[ia]) * e5m2_to_float(B[s].h8[ib]) +
+                  (double)e5m2_to_float(A[s].h8[ia]) * e5m2_to_float(B[s].l8[ib]);
+            fu += (double)A[s].x[ia] * (double)B[s].x[ib];
+          }
+        }
+        double ex = passes >= 3 ? hh + cr * inv : hh;
+        double got = out[((size_t)m * M + i) * N + j];
+        double ee = fabs(got - ex);
+        if (!(ee == ee)) ee = 1e30;
+        if (ee > max_err_exact) max_err_exact = ee;
+        if (got == got) { se_full += (got - fu) * (got - fu); s_full += fu * fu; }
+        if (fabs(ex) > max_ref) max_ref = fabs(ex);
+        if (ee > 1e-4 * sqrt((double)K * nsets)) {
+          if (!bad) { fb[0] = m; fb[1] = i; fb[2] = j; }
+          ++bad;
+        }
+      }
+  double flops = 2.0 * models * M * N * (double)K * nsets;
+  bool ok = bad == 0;
+  fflush(stdout);
+  printf("[%s] %s  models=%d M=%d N=%d K=%d sets=%d passes=%d  max|err| vs plane-exact %.3e (max|ref| %.2f), rel. rms "
+         "vs fp32 product %.2e  %.3f ms  %.1f TF algorithmic\n",
+         name, ok ? "PASS" : "FAIL", models, M, N, K, nsets, passes, max_err_exact, max_ref,
+         sqrt(se_full / (s_full + 1e-300)), ms, flops / ms * 1e-9);
+  if (!ok) {
+    printf("    %lld bad samples; first at model %d row %d col %d: got %.6f\n", bad, fb[0], fb[1], fb[2],
+           out[((size_t)fb[0] * M + fb[1]) * N + fb[2]]);
+  }
+  for (int s = 0; s < nsets; ++s) {
+    cudaFree(A[s].d_h); cudaFree(A[s].d_h8); cudaFree(A[s].d_l8);
+    cudaFree(B[s].d_h); cudaFree(B[s].d_h8); cudaFree(B[s].d_l8);
+  }
+  cudaFree(d_out);
+  return ok;
+}
+
 int main(int argc, char** argv) {
   bool big = argc > 1 && !strcmp(argv[1], "--big");
+  bool f8only = argc > 1 && !strcmp(argv[1], "--f8");
+  bool f8big = argc > 1 && !strcmp(argv[1], "--f8big");
+  setvbuf(stdout, nullptr, _IOLBF, 0);
   int dev = 0;
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, dev));
   printf("device: %s  sm_%d%d  SMs=%d\n", prop.name, prop.major, prop.minor,
          prop.multiProcessorCount);
   bool ok = true;
+  if (f8only || f8big || argc == 1) {
+    // ---- f16f8 arithmetic: each operand-major combination the engine uses, single CTA then CTA pairs
+    if (!f8big) {
+    ok &= run_case_f8<256, 64, false, false, 4, false>("f8_kk_hh", 1, 128, 256, 64, 1, 1, false, false);
+    ok &= run_case_f8<256, 64, false, false, 4, false>("f8_kk_k64", 1, 128, 256, 64, 1, 3, false, false);
+    ok &= run_case_f8<256, 64, false, false, 4, false>("f8_kk_multi", 3, 384, 512, 512, 1, 3, true, false);
+    ok &= run_case_f8<256, 32, false, false, 6, false>("f8_kk32_multi", 3, 384, 512, 512, 1, 3, true, false);
+    ok &= run_case_f8<256, 64, false, true, 4, false>("f8_kmn_k64", 1, 128, 256, 64, 1, 3, false, false);
+    ok &= run_case_f8<256, 64, false, true, 4, false>("f8_kmn_multi", 2, 256, 512, 512, 1, 3, false, false);
+    ok &= run_case_f8<256, 64, true, true, 4, false>("f8_mnmn_k64", 1, 128, 256, 64, 1, 3, false, false);
+    ok &= run_case_f8<256, 64, true, true, 4, false>("f8_mnmn_2set", 2, 256, 512, 320, 2, 3, false, true);
+    ok &= run_case_f8<256, 64, false, false, 6, true>("f8_pair_kk_multi", 3, 768, 512, 512, 1, 3, true, false);
+    ok &= run_case_f8<256, 64, false, false, 6, true>("f8_pair_kk_ragged", 2, 200, 328, 104, 1, 3, true, false);
+    ok &= run_case_f8<256, 64, false, true, 6, true>("f8_pair_kmn", 2, 512, 512, 512, 1, 3, false, false);
+    ok &= run_case_f8<256, 64, false, true, 6, true>("f8_pair_kmn_ragged", 2, 200, 328, 104, 1, 3, false, false);
+    ok &= run_case_f8<256, 64, true, true, 6, true>("f8_pair_mnmn_2set", 2, 512, 512, 320, 2, 3, false, true);
+    ok &= run_case_f8<256, 64, true, true, 6, true>("f8_pair_mnmn_ragged", 2, 200, 328, 104, 2, 3, false, true);
+    ok &= run_case_f8<256, 32, true, true, 8, true>("f8_pair_mnmn32", 2, 512, 512, 320, 2, 3, false, true);
+    }
+    if (f8big) {
+      // same-box comparison: the bf16x3 kernels the engine uses today (3 passes) at config-2 shapes
+      ok &= run_case<256, 64, false, false, 3, false, true>("bf_big_encode", 4, 8192, 4096, 512, 1, 3, true, false, 10);
+      ok &= run_case<256, 32, false, true, 6, false, true>("bf_big_decode", 4, 8192, 512, 4096, 1, 3, false, false, 10);
+      ok &= run_case<256, 32, true, true, 6, true, true>("bf_big_dw", 4, 4096, 512, 8192, 2, 3, false, true, 10);
+      ok &= run_case_f8<256, 64, false, false, 6, true>("f8_big_encode", 4, 8192, 4096, 512, 1, 3, true, false, 10);
+      ok &= run_case_f8<256, 64, false, true, 6, true>("f8_big_decode", 4, 8192, 512, 4096, 1, 3, false, false, 10);
+      ok &= run_case_f8<256, 64, true, true, 6, true>("f8_big_dw", 4, 4096, 512, 8192, 2, 3, false, true, 10);
+      ok &= run_case_f8<256, 32, true, true, 8, true>("f8_big_dw32", 4, 4096, 512, 8192, 2, 3, false, true, 10);
+      ok &= run_case_f8<256, 64, false, false, 6, true>("f8_big_enc_hh", 4, 8192, 4096, 512, 1, 1, true, false, 10);
+    }
+    if (f8only || f8big) {
+      printf(ok ? "ALL PASS\n" : "SOME FAILED\n");
+      return ok ? 0 : 1;
+    }
+  }
   // ---- K-major x K-major (encode / dC shape), increasing complexity
   ok &= run_case<256, 64, false, false, 2>("kk_k16", 1, 128, 256, 16, 1, 1, false, false);
   ok &= run_case<256, 64, false, false, 2>("kk_k64", 1, 128, 256, 64, 1, 1, false, false);
