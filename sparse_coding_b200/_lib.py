@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsce.so")
+# SCE_LIB: an alternative build of the same library (kernel A/B experiments, tools/ab_variants.sh)
+LIB_PATH = os.environ.get("SCE_LIB") or os.path.join(_HERE, "libsce.so")
 
 SCE_TIED, SCE_UNTIED, SCE_TOPK = 0, 1, 2
 SCE_ADAM_FROZEN_T1, SCE_ADAM_STANDARD = 0, 1

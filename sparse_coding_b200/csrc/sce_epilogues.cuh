@@ -145,6 +145,8 @@ struct EpiEncodeT {
     const float* bias = P.bias ? P.bias + (long long)T.model * n_total + col : nullptr;
     float ls = 0.f;
     int cnt = 0;
+    [[maybe_unused]] float zmin = 1.f;
+    [[maybe_unused]] uint32_t neg = 0;
     if (col + 32 <= n_total && !P.mask && bias) {
       // fast path: whole chunk in range, no coefficient mask; bias fetched as 8 uniform float4
 #pragma unroll
@@ -154,20 +156,45 @@ struct EpiEncodeT {
 #pragma unroll
         for (int u = 0; u < 4; u += 2) {
           const float z0 = __uint_as_float(r[j + u]) + bb[u], z1 = __uint_as_float(r[j + u + 1]) + bb[u + 1];
-          const bool p0 = z0 > 0.f, p1 = z1 > 0.f;
-          const float c0 = p0 ? z0 : 0.f, c1 = p1 ? z1 : 0.f;
-          split_pair<ARITH>(c0, c1, (j + u) >> 1, whi, wlo);
-          uint32_t& h2 = whi[(j + u) >> 1];
           if constexpr (ARITH == kArithF16F8) {
-            if (p0 && (h2 & 0xFFFFu) == 0u) h2 |= 0x00000001u;
-            if (p1 && (h2 >> 16) == 0u) h2 |= 0x00010000u;
+            // lean common case (the epilogue, not the tensor pipe, bounds this GEMM once the main loop is 2 pass
+            // equivalents): relu as max, activity count from the sign bits, and ONE tracker — the smallest |z| —
+            // for the two rare per-element fix-ups (exact zeros, positives below the fp16 range), done after the loop
+            zmin = fminf(zmin, fminf(fabsf(z0), fabsf(z1)));
+            neg = __funnelshift_l(__float_as_uint(z1), __funnelshift_l(__float_as_uint(z0), neg, 1), 1);
+            const float c0 = fmaxf(z0, 0.f), c1 = fmaxf(z1, 0.f);
+            split_pair<ARITH>(c0, c1, (j + u) >> 1, whi, wlo);
+            ls += c0 + c1;
+          } else {
+            const bool p0 = z0 > 0.f, p1 = z1 > 0.f;
+            const float c0 = p0 ? z0 : 0.f, c1 = p1 ? z1 : 0.f;
+            split_pair<ARITH>(c0, c1, (j + u) >> 1, whi, wlo);
+            uint32_t& h2 = whi[(j + u) >> 1];
+            if (P.flag_zero) {
+              if (z0 == 0.f) h2 |= 0x00008000u;
+              if (z1 == 0.f) h2 |= 0x80000000u;
+            }
+            ls += c0 + c1;
+            cnt += int(p0) + int(p1);
           }
-          if (P.flag_zero) {
-            if (z0 == 0.f) h2 |= 0x00008000u;
-            if (z1 == 0.f) h2 |= 0x80000000u;
+        }
+      }
+      if constexpr (ARITH == kArithF16F8) {
+        cnt = 32 - __popc(neg);  // no zeros among the 32 scores: positive <=> sign bit clear (fixed below otherwise)
+        if (zmin < 5.9604645e-8f) {  // 2^-24: some |z| is zero or rounds to zero in fp16 — redo the flags per element
+          cnt = 0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float z = __uint_as_float(r[j]) + __ldg(bias + j);
+            const uint32_t sh = (j & 1) * 16;
+            uint32_t& h2 = whi[j >> 1];
+            if (z > 0.f) {
+              ++cnt;
+              if (((h2 >> sh) & 0xFFFFu) == 0u) h2 |= 1u << sh;
+            } else if (z == 0.f && P.flag_zero) {
+              h2 |= 0x8000u << sh;
+            }
           }
-          ls += c0 + c1;
-          cnt += int(p0) + int(p1);
         }
       }
     } else {
@@ -352,17 +379,33 @@ struct EpiDcodeT {
     if (col >= n_total) return;  // warp-uniform
     float dz[32];
     uint32_t whi[16], wlo[16];
+    // bf16 / fp16 bit patterns of the code: 0x0001..0x7FFF positive (c > 0); 0x8000 is the "z == 0" flag written by
+    // encode (gradient passes, no sparsity term). No flag among this thread's 32 coefficients (the common case):
+    // active <=> the 16-bit pattern is non-zero.
+    uint32_t any = 0;
 #pragma unroll
-    for (int j = 0; j < 32; j += 2) {
-      // bf16 / fp16 bit patterns: 0x0001..0x7FFF positive (c > 0); 0x8000 is the "z == 0" flag written by encode
-      const uint32_t b0 = cw[j >> 1] & 0xFFFFu, b1 = cw[j >> 1] >> 16;
-      const bool pos0 = (b0 - 1u) < 0x7FFFu, pos1 = (b1 - 1u) < 0x7FFFu;
-      const bool gate0 = (b0 - 1u) < 0x8000u, gate1 = (b1 - 1u) < 0x8000u;
-      const float v0 = gate0 ? __uint_as_float(r[j]) + (pos0 ? aB : 0.f) : 0.f;
-      const float v1 = gate1 ? __uint_as_float(r[j + 1]) + (pos1 ? aB : 0.f) : 0.f;
-      dz[j] = v0;
-      dz[j + 1] = v1;
-      split_pair<ARITH>(v0, v1, j >> 1, whi, wlo);
+    for (int j = 0; j < 16; ++j) any |= cw[j];
+    if ((any & 0x80008000u) == 0u) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 2) {
+        const float v0 = (cw[j >> 1] & 0x0000FFFFu) ? __uint_as_float(r[j]) + aB : 0.f;
+        const float v1 = (cw[j >> 1] & 0xFFFF0000u) ? __uint_as_float(r[j + 1]) + aB : 0.f;
+        dz[j] = v0;
+        dz[j + 1] = v1;
+        split_pair<ARITH>(v0, v1, j >> 1, whi, wlo);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; j += 2) {
+        const uint32_t b0 = cw[j >> 1] & 0xFFFFu, b1 = cw[j >> 1] >> 16;
+        const bool pos0 = (b0 - 1u) < 0x7FFFu, pos1 = (b1 - 1u) < 0x7FFFu;
+        const bool gate0 = (b0 - 1u) < 0x8000u, gate1 = (b1 - 1u) < 0x8000u;
+        const float v0 = gate0 ? __uint_as_float(r[j]) + (pos0 ? aB : 0.f) : 0.f;
+        const float v1 = gate1 ? __uint_as_float(r[j + 1]) + (pos1 ? aB : 0.f) : 0.f;
+        dz[j] = v0;
+        dz[j + 1] = v1;
+        split_pair<ARITH>(v0, v1, j >> 1, whi, wlo);
+      }
     }
     stage_and_store<ARITH>(stage, T.lane, whi, wlo, &P.out_hi, &P.out_lo, &P.out_x8, col,
                            T.m_blk * kBM + T.warp_q * 32, T.model);

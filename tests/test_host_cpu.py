@@ -39,6 +39,22 @@ def test_abi_validation_without_device():
     desc.d = 63                                                      # not a multiple of 8
     assert lib.sce_workspace_bytes(C.byref(desc)) == 0
     assert b"multiples of 8" in lib.sce_last_error()
+    # operand arithmetic (sce_arith): both carry 4 bytes per operand element, so the workspace does not depend on it;
+    # f16f8 needs 16-byte row pitches in its 8-bit planes, AUTO falls back to bf16x3 where that fails
+    desc.d = 64
+    sizes = []
+    for arith in (_lib.SCE_ARITH_AUTO, _lib.SCE_ARITH_BF16X3, _lib.SCE_ARITH_F16F8):
+        desc.arith = arith
+        sizes.append(lib.sce_workspace_bytes(C.byref(desc)))
+    assert sizes[0] > 0 and max(sizes) - min(sizes) <= 64 * 1024, sizes
+    desc.d, desc.arith = 72, _lib.SCE_ARITH_F16F8                    # multiple of 8 but not of 16
+    assert lib.sce_workspace_bytes(C.byref(desc)) == 0
+    assert b"multiples of 16" in lib.sce_last_error()
+    desc.arith = _lib.SCE_ARITH_AUTO
+    assert lib.sce_workspace_bytes(C.byref(desc)) > 0
+    desc.arith = 7
+    assert lib.sce_workspace_bytes(C.byref(desc)) == 0
+    desc.arith = _lib.SCE_ARITH_AUTO
     desc.d = 64
     desc.fwd_passes = 2
     assert lib.sce_workspace_bytes(C.byref(desc)) == 0
