@@ -382,6 +382,8 @@ def main():
                          "peak_source": pk["source"], "alg_flops_per_launch": alg_flops_dw,
                          "ms_per_launch": dw_ms,
                          "issued_tflops": alg_flops_dw * bwd_eq / (dw_ms * 1e-3) / 1e12 if dw_ms > 0 else None,
+                         "issued_note": f"{bwd_eq} bf16-pass equivalents per fp32 GEMM ({arith}): frac <= 1/{bwd_eq} by "
+                                        "construction; issued_tflops / peak is the tensor-pipe utilisation",
                          "step_alg_tflops": step_flops / (ms / K * 1e-3) / 1e12},
             "phases_ms": per_phase,
             # every GEMM phase against the same peak: algorithmic (fp32-equivalent) and issued (x passes) TFLOP/s
@@ -392,7 +394,7 @@ def main():
                                                 ("dw", 2, bwd_eq)) if per_phase[ph] > 0},
             "final_loss_mean": float(final_loss.mean()),
         }
-        tr = ncu_traffic()
+        tr = (ncu_traffic() or {}).get(arith)
         if tr:
             line["roofline"]["traffic"] = tr["dw_dram_bytes_per_launch"]
             line["roofline"]["traffic_source"] = tr["source"]
