@@ -51,9 +51,14 @@ def make_models(sig, M, d, n, seed):
     return [sig.init(d, n, a) for a in l1_grid(M)]
 
 
+ACT_FP16 = True   # --act-precision: values as the reference caches them (fp16, activation_dataset.py:404-412) or raw fp32
+
+
 def synth_batches(n_batches, B, d, seed, pin=False):
     """Sparse-mixture activations (the distribution of sc_datasets/random_dataset.py:76-142): a few unit features
-    per row + noise, so that ReLU sparsity is non-trivial. Returns CPU tensors."""
+    per row + noise, so that ReLU sparsity is non-trivial. Returns CPU fp32 tensors; with ACT_FP16 the VALUES are
+    rounded to fp16 first, which is what a chunk written by the reference's harvester and loaded by big_sweep.py
+    (`torch.load(chunk_loc).to(device="cpu", dtype=torch.float32)`, big_sweep.py:358) contains."""
     gen = torch.Generator().manual_seed(seed)
     feats = torch.randn(2048, d, generator=gen)
     feats /= feats.norm(dim=-1, keepdim=True)
@@ -61,6 +66,8 @@ def synth_batches(n_batches, B, d, seed, pin=False):
     for _ in range(n_batches):
         codes = (torch.rand(B, 2048, generator=gen) < 0.01).float() * torch.rand(B, 2048, generator=gen)
         x = codes @ feats + 0.05 * torch.randn(B, d, generator=gen)
+        if ACT_FP16:
+            x = x.half().float()
         out.append(x.pin_memory() if pin else x)
     return out
 
@@ -229,9 +236,14 @@ def main():
     ap.add_argument("--bwd-passes", type=int, default=3, choices=[1, 3])
     ap.add_argument("--arith", default="auto", choices=["auto", "bf16x3", "f16f8"],
                     help="operand arithmetic (include/sce.h sce_arith); auto = f16f8 where the shape allows")
+    ap.add_argument("--act-precision", default="fp16", choices=["fp16", "fp32"],
+                    help="synthetic activation VALUES: fp16-representable (the reference's chunk format; default) or "
+                         "arbitrary fp32. The tensors fed to the engine are fp32 either way.")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-alt", action="store_true", help="skip the informational single-pass-backward run")
     args = ap.parse_args()
+    global ACT_FP16
+    ACT_FP16 = args.act_precision == "fp16"
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -366,8 +378,11 @@ def main():
             "metric": METRIC, "value": value, "unit": "activations/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32",
-            "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {desc}", "models_per_gpu": M, "d_model": d, "dict_size": n,
+            "data": "synthetic (sparse mixture + noise); values " +
+                    ("rounded to fp16 as the reference caches activations (activation_dataset.py:404-412), "
+                     if ACT_FP16 else "arbitrary fp32, ") + "fed as fp32 tensors",
+            "config": {"workload": f"{args.workload}: {desc}", "models_per_gpu": M,
+                       "activation_values": args.act_precision, "d_model": d, "dict_size": n,
                        "batch": B, "parallelism": f"ensemble-shard x{world}" if world > 1 else "single GPU",
                        "arith": arith, "arithmetic": arith_text, "pass_equivalents_per_gemm": full_passes,
                        "fwd_passes": 3, "bwd_passes": args.bwd_passes, "adam_count_mode": "frozen_t1",

@@ -72,6 +72,7 @@ struct sce_plan {
   __nv_bfloat16 *g_hi, *g_lo;     // [M, Bmax, d]
   __nv_bfloat16 *dz_hi, *dz_lo;   // [M, Bmax, n]   (top-k: fp32 scores alias these planes)
   uint8_t *x_x8, *wenc_x8, *wdec_x8, *c_x8, *g_x8, *dz_x8;
+  uint32_t* res_flags;            // [0]: the batch has a non-zero residual plane (f16f8; written by the batch split)
   float *dw_enc, *dw_dec;         // [M, n, d]
   float *part_enc, *part_dec, *db_part, *bnorm, *l1_over_b, *loss_stage, *nnz_stage;
   int tiles_mB_max;
@@ -181,6 +182,7 @@ static size_t carve(sce_plan* p, const sce_desc& d, uint8_t* base) {
   auto lob = c.take<float>(M);
   auto ls = c.take<float>(M * 4);
   auto ns = c.take<float>(M);
+  auto rf = c.take<uint32_t>(8);
   if (p) {
     p->x_stage = X;
     p->x_hi = xh;
@@ -210,6 +212,7 @@ static size_t carve(sce_plan* p, const sce_desc& d, uint8_t* base) {
     p->l1_over_b = lob;
     p->loss_stage = ls;
     p->nnz_stage = ns;
+    p->res_flags = rf;
     p->tiles_mB_max = (int)tiles_mB;
   }
   return align_up(c.off, 1024);
@@ -352,11 +355,17 @@ static int build_maps(sce_plan* p, int B, BatchMaps** out) {
 // ------------------------------------------------------------------------------------------------
 // GEMM launcher
 // ------------------------------------------------------------------------------------------------
+// device flags "this operand's residual plane is all zeros" (f16f8; GemmParams::a_res_flag), nullptr = unknown
+struct ResFlags {
+  const uint32_t* a[kMaxSets] = {nullptr, nullptr};
+  const uint32_t* b[kMaxSets] = {nullptr, nullptr};
+};
+
 template <class Epi, int BN, int BK, bool A_MN, bool B_MN, int STAGES, bool SPLIT_ACC = false, bool CTA2 = false,
           int ARITH = kArithBf16x3>
 static int launch_gemm_t(const sce_plan* p, const GemmMaps& maps, int nsets, const int* a_batched,
                          const int* b_batched, int k_total, int passes, int m_total, int n_total,
-                         const typename Epi::Params& epi, cudaStream_t st) {
+                         const typename Epi::Params& epi, cudaStream_t st, const ResFlags& rf = ResFlags()) {
   using SM = GemmSmem<BN, BK, A_MN, B_MN, STAGES, Epi::kWarpStageBytes, CTA2, ARITH>;
   auto kern = gemm_split_kernel<Epi, BN, BK, A_MN, B_MN, STAGES, SPLIT_ACC, CTA2, ARITH>;
   // the opt-in to > 48 KB of dynamic shared memory is per device: remember which devices have it
@@ -376,6 +385,8 @@ static int launch_gemm_t(const sce_plan* p, const GemmMaps& maps, int nsets, con
     gp.b_x8[s] = maps.b_x8[s];
     gp.a_batched[s] = a_batched[s];
     gp.b_batched[s] = b_batched[s];
+    gp.a_res_flag[s] = rf.a[s];
+    gp.b_res_flag[s] = rf.b[s];
   }
   gp.nsets = nsets;
   gp.k_total = k_total;
@@ -510,6 +521,7 @@ static int run_pipeline_t(sce_plan* p, const float* x, int B, float* x_hat, bool
 
   prof_mark(p, SCE_PHASE_SPLIT, st);
   // ---- x -> (hi, lo): per model slabs are batch_max apart in the workspace
+  if constexpr (f8) CUDA_TRY(cudaMemsetAsync(p->res_flags, 0, sizeof(uint32_t), st));
   for (int m = 0; m < p->xm; ++m) {
     const long long n4 = (long long)B * dd / 4;
     const int blocks = (int)((n4 + 255) / 256 < 2048 ? (n4 + 255) / 256 : 2048);
@@ -517,7 +529,7 @@ static int run_pipeline_t(sce_plan* p, const float* x, int B, float* x_hat, bool
     split_rows_kernel<AR><<<blocks, 256, 0, st>>>(
         x + (long long)m * B * dd, p->x_hi + m * Bm * dd,
         f8 ? (void*)(reinterpret_cast<uint8_t*>(p->x_lo) + m * Bm * dd) : (void*)(p->x_lo + m * Bm * dd),
-        f8 ? (void*)(p->x_x8 + m * Bm * dd) : nullptr, n4);
+        f8 ? (void*)(p->x_x8 + m * Bm * dd) : nullptr, n4, f8 ? p->res_flags : nullptr);
     ++launches;
   }
   CUDA_TRY(cudaGetLastError());
@@ -527,6 +539,12 @@ static int run_pipeline_t(sce_plan* p, const float* x, int B, float* x_hat, bool
   // the f16f8 kernels run narrow outputs on single CTAs (build_maps)
   auto pair_ok = [&](int flag, int rows, int out_cols) { return use_pair(flag, rows) && !(f8 && out_cols <= 128); };
 
+  // the batch's residual-plane flag, for the GEMMs that read x as their A (encode) or B (weight gradient, set 0) operand
+  ResFlags x_is_a, x_is_b;
+  if constexpr (f8) {
+    x_is_a.a[0] = p->res_flags;
+    x_is_b.b[0] = p->res_flags;
+  }
   // ---- encode
   prof_mark(p, SCE_PHASE_ENCODE, st);
   int n_enc_parts;
@@ -542,7 +560,7 @@ static int run_pipeline_t(sce_plan* p, const float* x, int B, float* x_hat, bool
     ep.flag_zero = 1;
     ep.tiles_n = n > 128 ? (n + 255) / 256 : 1;
     rc = launch_k<EpiEnc, false, false, AR>(n > 128, p->bk_encode, pair_ok(p->pair_encode, B, n), p, maps->encode, 1, xb, one,
-                                            dd, d.fwd_passes, B, n, ep, st);
+                                            dd, d.fwd_passes, B, n, ep, st, x_is_a);
     if (rc) return rc;
     ++launches;
     n_enc_parts = tiles_mB * 8 * ep.tiles_n;
@@ -554,7 +572,7 @@ static int run_pipeline_t(sce_plan* p, const float* x, int B, float* x_hat, bool
     sp.ld = n;
     sp.scale = 1.f;
     rc = launch_k<EpiStoreF32, false, false, AR>(n > 128, p->bk_encode, pair_ok(p->pair_encode, B, n), p, maps->encode, 1, xb,
-                                                 one, dd, d.fwd_passes, B, n, sp, st);
+                                                 one, dd, d.fwd_passes, B, n, sp, st, x_is_a);
     if (rc) return rc;
     ++launches;
     if ((size_t)n * 4 > 200 * 1024) return fail(SCE_ERR_INVALID, "top-k: n = %d exceeds the shared-memory row buffer", n);
@@ -629,7 +647,7 @@ static int run_pipeline_t(sce_plan* p, const float* x, int B, float* x_hat, bool
 
     // ---- weight gradients
     prof_mark(p, SCE_PHASE_DW, st);
-    auto dw = [&](const GemmMaps& gm, int nsets, const int* ab, const int* bb, float* out) -> int {
+    auto dw = [&](const GemmMaps& gm, int nsets, const int* ab, const int* bb, float* out, const ResFlags& rf) -> int {
       EpiStoreF32::Params sp;
       sp.out = out;
       sp.model_stride = (long long)n * dd;
@@ -638,9 +656,9 @@ static int run_pipeline_t(sce_plan* p, const float* x, int B, float* x_hat, bool
       const bool pair = pair_ok(p->pair_dw, n, dd);
       if constexpr (f8) {
         if (dd > 128)
-          return pair ? launch_gemm_t<EpiStoreF32, 256, kBkF8, true, true, 6, false, true, kArithF16F8>(p, gm, nsets, ab, bb, B, p->dw_passes, n, dd, sp, st)
-                      : launch_gemm_t<EpiStoreF32, 256, kBkF8, true, true, 4, false, false, kArithF16F8>(p, gm, nsets, ab, bb, B, p->dw_passes, n, dd, sp, st);
-        return launch_gemm_t<EpiStoreF32, 128, kBkF8, true, true, 6, false, false, kArithF16F8>(p, gm, nsets, ab, bb, B, p->dw_passes, n, dd, sp, st);
+          return pair ? launch_gemm_t<EpiStoreF32, 256, kBkF8, true, true, 6, false, true, kArithF16F8>(p, gm, nsets, ab, bb, B, p->dw_passes, n, dd, sp, st, rf)
+                      : launch_gemm_t<EpiStoreF32, 256, kBkF8, true, true, 4, false, false, kArithF16F8>(p, gm, nsets, ab, bb, B, p->dw_passes, n, dd, sp, st, rf);
+        return launch_gemm_t<EpiStoreF32, 128, kBkF8, true, true, 6, false, false, kArithF16F8>(p, gm, nsets, ab, bb, B, p->dw_passes, n, dd, sp, st, rf);
       }
       if (dd > 128)
         return pair ? launch_gemm_t<EpiStoreF32, 256, kBkDw, true, true, 6, true, true>(p, gm, nsets, ab, bb, B, p->dw_passes, n, dd, sp, st)
@@ -649,14 +667,14 @@ static int run_pipeline_t(sce_plan* p, const float* x, int B, float* x_hat, bool
                   : launch_gemm_t<EpiStoreF32, 128, kBkDw, true, true, 6, true, false>(p, gm, nsets, ab, bb, B, p->dw_passes, n, dd, sp, st);
     };
     if (d.variant == SCE_UNTIED) {
-      rc = dw(maps->dw_enc, 1, one, xb, p->dw_enc);
+      rc = dw(maps->dw_enc, 1, one, xb, p->dw_enc, x_is_b);
       if (rc) return rc;
-      rc = dw(maps->dw_dec, 1, one, one, p->dw_dec);
+      rc = dw(maps->dw_dec, 1, one, one, p->dw_dec, ResFlags());
       if (rc) return rc;
       launches += 2;
     } else {
       const int bb[2] = {xb[0], 1};
-      rc = dw(maps->dw_enc, 2, one, bb, p->dw_enc);
+      rc = dw(maps->dw_enc, 2, one, bb, p->dw_enc, x_is_b);
       if (rc) return rc;
       ++launches;
     }

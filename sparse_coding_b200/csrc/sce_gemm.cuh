@@ -41,6 +41,12 @@ struct GemmParams {
   // bf16x3: (hi, lo) bf16 planes. f16f8: hi = fp16 plane, lo = e5m2(x) plane, x8 = e5m2((x - fp16(x)) * 2^kLoShift) plane.
   CUtensorMap a_hi[kMaxSets], a_lo[kMaxSets], b_hi[kMaxSets], b_lo[kMaxSets];
   CUtensorMap a_x8[kMaxSets], b_x8[kMaxSets];
+  // f16f8: optional device flags, one per operand: *flag == 0 says "the residual plane (x8) of this operand is all
+  // zeros for this launch" (e.g. activations that are exactly fp16, the reference's chunk format). The cross term that
+  // multiplies that plane is then skipped together with the loads of its two planes: 25 % fewer operand bytes and
+  // 8-bit instructions for that operand pair, bit-identical results. nullptr = no such knowledge.
+  const uint32_t* a_res_flag[kMaxSets];
+  const uint32_t* b_res_flag[kMaxSets];
   int a_batched[kMaxSets], b_batched[kMaxSets];  // 0: operand shared by all models
   int nsets;      // number of (A,B) operand pairs accumulated into the same tile
   int k_total;    // reduction length of each pair
@@ -162,6 +168,15 @@ gemm_split_kernel(const __grid_constant__ GemmParams<typename Epi::Params> p) {
   if constexpr (CTA2) cluster_sync_all();  // the peer's barriers must be initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  // f16f8: which cross terms each operand pair needs (see GemmParams::a_res_flag); the same for every CTA of the launch
+  [[maybe_unused]] bool term_lh[kMaxSets], term_hl[kMaxSets];
+  if constexpr (F8) {
+#pragma unroll
+    for (int s = 0; s < kMaxSets; ++s) {
+      term_lh[s] = s < p.nsets && (p.a_res_flag[s] == nullptr || __ldg(p.a_res_flag[s]) != 0u);
+      term_hl[s] = s < p.nsets && (p.b_res_flag[s] == nullptr || __ldg(p.b_res_flag[s]) != 0u);
+    }
+  }
 
   if (warp == 0) {
     // ======================= TMA producer =======================
@@ -187,10 +202,14 @@ gemm_split_kernel(const __grid_constant__ GemmParams<typename Epi::Params> p) {
             for (int set = 0; set < p.nsets; ++set) {
               const int am = p.a_batched[set] ? model : 0;
               const int bm = p.b_batched[set] ? model : 0;
+              // cross terms of this operand pair: t_lh = A.l8 x B.h8 (needs A's residual), t_hl = A.h8 x B.l8
+              const bool t_lh = term_lh[set], t_hl = term_hl[set];
+              if (sweep == 0 && !t_lh && !t_hl) continue;
+              const uint32_t bytes = sweep == 1 ? stage_bytes : (uint32_t(t_lh) + uint32_t(t_hl)) * (stage_bytes / 2);
               for (int kb = 0; kb < kblocks; ++kb) {
                 mbar_wait(&empty_bar[stage], phase ^ 1);
                 uint8_t* st = smem + stage * SM::kStage;
-                if (!CTA2 || cta_rank == 0) mbar_expect_tx(&full_bar[stage], CTA2 ? 2 * stage_bytes : stage_bytes);
+                if (!CTA2 || cta_rank == 0) mbar_expect_tx(&full_bar[stage], CTA2 ? 2 * bytes : bytes);
                 const int k0 = kb * BK;
                 if (sweep == 1) {
                   uint8_t* sa = st;
@@ -213,22 +232,22 @@ gemm_split_kernel(const __grid_constant__ GemmParams<typename Epi::Params> p) {
                   uint8_t* sb_h = st + SM::kATile;
                   uint8_t* sb_l = sb_h + SM::kBTile / 2;
                   if constexpr (!A_MN) {
-                    load(sa_h, &p.a_lo[set], &full_bar[stage], k0, m_blk * kBM, am);
-                    load(sa_l, &p.a_x8[set], &full_bar[stage], k0, m_blk * kBM, am);
+                    if (t_hl) load(sa_h, &p.a_lo[set], &full_bar[stage], k0, m_blk * kBM, am);
+                    if (t_lh) load(sa_l, &p.a_x8[set], &full_bar[stage], k0, m_blk * kBM, am);
                   } else {
                     static_assert(!F8 || !A_MN || kBM == 128, "one 128-element box per MN-major 8-bit A tile");
-                    load(sa_h, &p.a_lo[set], &full_bar[stage], m_blk * kBM, k0, am);
-                    load(sa_l, &p.a_x8[set], &full_bar[stage], m_blk * kBM, k0, am);
+                    if (t_hl) load(sa_h, &p.a_lo[set], &full_bar[stage], m_blk * kBM, k0, am);
+                    if (t_lh) load(sa_l, &p.a_x8[set], &full_bar[stage], m_blk * kBM, k0, am);
                   }
                   if constexpr (!B_MN) {
-                    load(sb_h, &p.b_lo[set], &full_bar[stage], k0, b_row0, bm);
-                    load(sb_l, &p.b_x8[set], &full_bar[stage], k0, b_row0, bm);
+                    if (t_lh) load(sb_h, &p.b_lo[set], &full_bar[stage], k0, b_row0, bm);
+                    if (t_hl) load(sb_l, &p.b_x8[set], &full_bar[stage], k0, b_row0, bm);
                   } else {
                     static_assert(!F8 || !B_MN || kBHalf % 128 == 0, "MN-major 8-bit B tiles come in 128-element boxes");
 #pragma unroll
                     for (int j = 0; j < kBHalf / 128; ++j) {
-                      load(sb_h + j * (BK * 128), &p.b_lo[set], &full_bar[stage], b_row0 + j * 128, k0, bm);
-                      load(sb_l + j * (BK * 128), &p.b_x8[set], &full_bar[stage], b_row0 + j * 128, k0, bm);
+                      if (t_lh) load(sb_h + j * (BK * 128), &p.b_lo[set], &full_bar[stage], b_row0 + j * 128, k0, bm);
+                      if (t_hl) load(sb_l + j * (BK * 128), &p.b_x8[set], &full_bar[stage], b_row0 + j * 128, k0, bm);
                     }
                   }
                 }
@@ -322,7 +341,10 @@ gemm_split_kernel(const __grid_constant__ GemmParams<typename Epi::Params> p) {
           constexpr uint32_t a8_kstep = A_MN ? 4096 : 32, b8_kstep = B_MN ? 4096 : 32;  // bytes per K = 32 slice
           const int iters = p.nsets * kblocks;
           if (three) {
-            for (int it = 0; it < iters; ++it) {
+            for (int set = 0; set < p.nsets; ++set) {
+            const bool t_lh = term_lh[set], t_hl = term_hl[set];
+            if (!t_lh && !t_hl) continue;
+            for (int kb = 0; kb < kblocks; ++kb) {
               mbar_wait(&full_bar[stage], phase);
               tc_fence_after();
               const uint32_t sa_h = smem_u32(smem + stage * SM::kStage);
@@ -335,9 +357,14 @@ gemm_split_kernel(const __grid_constant__ GemmParams<typename Epi::Params> p) {
                 const uint64_t al = make_sdesc(sa_l + k * a8_kstep, a_lbo, a8_sbo, a8_lt);
                 const uint64_t bh = make_sdesc(sb_h + k * b8_kstep, b_lbo, b8_sbo, b8_lt);
                 const uint64_t bl = make_sdesc(sb_l + k * b8_kstep, b_lbo, b8_sbo, b8_lt);
-                umma_f8<CTA2>(d_tmem, al, bh, i8, accumulate);
-                umma_f8<CTA2>(d_tmem, ah, bl, i8, 1);
-                accumulate = 1;
+                if (t_lh) {
+                  umma_f8<CTA2>(d_tmem, al, bh, i8, accumulate);
+                  accumulate = 1;
+                }
+                if (t_hl) {
+                  umma_f8<CTA2>(d_tmem, ah, bl, i8, accumulate);
+                  accumulate = 1;
+                }
               }
               commit(&empty_bar[stage]);
               if (++stage == STAGES) {
@@ -345,8 +372,9 @@ gemm_split_kernel(const __grid_constant__ GemmParams<typename Epi::Params> p) {
                 phase ^= 1;
               }
             }
+            }
           }
-          bool rescale = three;
+          bool rescale = accumulate != 0;  // some cross term was accumulated (at 2^kLoShift): rescale with the first hh
           for (int it = 0; it < iters; ++it) {
             mbar_wait(&full_bar[stage], phase);
             tc_fence_after();

@@ -31,14 +31,30 @@ __device__ __forceinline__ void store_planes4(const float (&v)[4], void* hi, voi
   }
 }
 
+// f16f8: `res_flag` (zeroed by the caller) is set to 1 when any element has a non-zero residual plane entry, i.e. is
+// not exactly representable in fp16; the GEMMs that read x skip the corresponding cross term while it stays 0.
 template <int ARITH>
 __global__ void split_rows_kernel(const float* __restrict__ x, void* __restrict__ hi, void* __restrict__ lo,
-                                  void* __restrict__ x8, long long n4) {
+                                  void* __restrict__ x8, long long n4, uint32_t* __restrict__ res_flag) {
   const long long stride = (long long)gridDim.x * blockDim.x;
+  uint32_t any = 0;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
     const float4 v = reinterpret_cast<const float4*>(x)[i];
     const float vv[4] = {v.x, v.y, v.z, v.w};
-    store_planes4<ARITH>(vv, hi, lo, x8, i);
+    if constexpr (ARITH == kArithF16F8) {
+      uint2 h16;
+      uint32_t h8, l8;
+      split4_f16f8(vv, h16, h8, l8);
+      reinterpret_cast<uint2*>(hi)[i] = h16;
+      reinterpret_cast<uint32_t*>(lo)[i] = h8;
+      reinterpret_cast<uint32_t*>(x8)[i] = l8;
+      any |= l8 & 0x7F7F7F7Fu;   // (a residual of -0 is still zero)
+    } else {
+      store_planes4<ARITH>(vv, hi, lo, x8, i);
+    }
+  }
+  if constexpr (ARITH == kArithF16F8) {
+    if (res_flag && __any_sync(0xffffffffu, any != 0u) && (threadIdx.x & 31) == 0) *res_flag = 1u;  // benign race: all write 1
   }
 }
 

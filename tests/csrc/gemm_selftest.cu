@@ -261,13 +261,14 @@ struct OperandF8 {
   int pitch;  // elements between consecutive rows (K-major) / k (MN-major): multiple of 16, TMA strides are 16-byte units
   size_t idx(int m, int r, int k) const { return mn ? ((size_t)m * K + k) * pitch + r : ((size_t)m * rows + r) * pitch + k; }
 };
-static void make_operand_f8(OperandF8& o, int models, int rows, int K, bool mn, float scale) {
+static void make_operand_f8(OperandF8& o, int models, int rows, int K, bool mn, float scale, bool fp16_exact = false) {
   o.models = models; o.rows = rows; o.K = K; o.mn = mn;
   o.pitch = ((mn ? rows : K) + 15) / 16 * 16;
   size_t n = (size_t)models * (mn ? K : rows) * o.pitch;
   o.x.resize(n); o.h.resize(n); o.h8.resize(n); o.l8.resize(n);
   for (size_t i = 0; i < n; ++i) {
     float v = frand() * scale;
+    if (fp16_exact) v = __half2float(__float2half_rn(v));   // all-zero residual plane
     o.x[i] = v;
     o.h[i] = __float2half_rn(v);
     o.h8[i] = __nv_cvt_float_to_fp8(v, __NV_SATFINITE, __NV_E5M2);
@@ -294,12 +295,15 @@ static bool tmaps_f8(const OperandF8& o, uint32_t box_rows_kmajor, int BK, CUten
 
 template <int BN, int BK, bool A_MN, bool B_MN, int STAGES, bool CTA2>
 static bool run_case_f8(const char* name, int models, int M, int N, int K, int nsets, int passes, bool a_shared,
-                        bool b_shared, int reps = 1) {
+                        bool b_shared, int reps = 1, int exact = 0 /*1: A of set 0, 2: B of set 0 is fp16-exact + flagged*/) {
   OperandF8 A[2], B[2];
   for (int s = 0; s < nsets; ++s) {
-    make_operand_f8(A[s], a_shared ? 1 : models, M, K, A_MN, 3.0f);
-    make_operand_f8(B[s], b_shared ? 1 : models, N, K, B_MN, 0.25f);
+    make_operand_f8(A[s], a_shared ? 1 : models, M, K, A_MN, 3.0f, s == 0 && exact == 1);
+    make_operand_f8(B[s], b_shared ? 1 : models, N, K, B_MN, 0.25f, s == 0 && exact == 2);
   }
+  uint32_t* d_flag = nullptr;   // "residual plane is all zeros" flag (GemmParams::a_res_flag / b_res_flag), value 0
+  CK(cudaMalloc(&d_flag, 4));
+  CK(cudaMemset(d_flag, 0, 4));
   float* d_out;
   size_t out_elems = (size_t)models * M * N;
   CK(cudaMalloc(&d_out, out_elems * 4));
@@ -315,6 +319,8 @@ static bool run_case_f8(const char* name, int models, int M, int N, int K, int n
     p.a_batched[s] = a_shared ? 0 : 1;
     p.b_batched[s] = b_shared ? 0 : 1;
   }
+  if (exact == 1) p.a_res_flag[0] = d_flag;
+  if (exact == 2) p.b_res_flag[0] = d_flag;
   p.nsets = nsets; p.k_total = K; p.passes = passes; p.n_models = models; p.m_total = M; p.n_total = N;
   const int tile_rows = CTA2 ? 2 * kBM : kBM;
   p.tiles_m = (M + tile_rows - 1) / tile_rows;
@@ -398,6 +404,7 @@ static bool run_case_f8(const char* name, int models, int M, int N, int K, int n
     cudaFree(B[s].d_h); cudaFree(B[s].d_h8); cudaFree(B[s].d_l8);
   }
   cudaFree(d_out);
+  cudaFree(d_flag);
   return ok;
 }
 
@@ -430,6 +437,11 @@ int main(int argc, char** argv) {
     ok &= run_case_f8<256, 64, true, true, 6, true>("f8_pair_mnmn_2set", 2, 512, 512, 320, 2, 3, false, true);
     ok &= run_case_f8<256, 64, true, true, 6, true>("f8_pair_mnmn_ragged", 2, 200, 328, 104, 2, 3, false, true);
     ok &= run_case_f8<256, 32, true, true, 8, true>("f8_pair_mnmn32", 2, 512, 512, 320, 2, 3, false, true);
+    // fp16-exact operand flagged "no residual plane": the cross term and the loads of its planes are skipped
+    ok &= run_case_f8<256, 64, false, false, 6, true>("f8_pair_kk_exactA", 3, 768, 512, 512, 1, 3, true, false, 1, 1);
+    ok &= run_case_f8<256, 64, false, false, 4, false>("f8_kk_exactA", 2, 200, 328, 104, 1, 3, true, false, 1, 1);
+    ok &= run_case_f8<256, 64, true, true, 6, true>("f8_pair_mnmn_exactB", 2, 512, 512, 320, 2, 3, false, true, 1, 2);
+    ok &= run_case_f8<256, 64, true, true, 4, false>("f8_mnmn_exactB", 2, 200, 328, 104, 2, 3, false, true, 1, 2);
     }
     if (f8big) {
       // same-box comparison: the bf16x3 kernels the engine uses today (3 passes) at config-2 shapes
@@ -441,6 +453,8 @@ int main(int argc, char** argv) {
       ok &= run_case_f8<256, 64, true, true, 6, true>("f8_big_dw", 4, 4096, 512, 8192, 2, 3, false, true, 10);
       ok &= run_case_f8<256, 32, true, true, 8, true>("f8_big_dw32", 4, 4096, 512, 8192, 2, 3, false, true, 10);
       ok &= run_case_f8<256, 64, false, false, 6, true>("f8_big_enc_hh", 4, 8192, 4096, 512, 1, 1, true, false, 10);
+      ok &= run_case_f8<256, 64, false, false, 6, true>("f8_big_encode_exactA", 4, 8192, 4096, 512, 1, 3, true, false, 10, 1);
+      ok &= run_case_f8<256, 64, true, true, 6, true>("f8_big_dw_exactB", 4, 4096, 512, 8192, 2, 3, false, true, 10, 2);
     }
     if (f8only || f8big) {
       printf(ok ? "ALL PASS\n" : "SOME FAILED\n");

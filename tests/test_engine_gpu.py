@@ -201,6 +201,44 @@ def test_exact_zero_rows_clamp_gradient():
     assert int(aux["c"].dense()[0, 5].count_nonzero()) == 0
 
 
+@pytest.mark.parametrize("kind", ["tied", "untied"])
+def test_fp16_exact_batches_skip_the_residual_term(kind):
+    """Activation chunks are fp16 on disk (activation_dataset.py:404-412): such a batch has an all-zero residual
+    plane, the batch-split kernel leaves the plan's flag at 0 and the encode / weight-gradient GEMMs skip the cross
+    term (and the loads) that multiply it. The flag is per step: exact and inexact batches may alternate, and every
+    step must match the oracle on ITS batch — a stale flag would drop a needed term (1e-3-level error) or keep a dead one."""
+    import sparse_coding_b200 as S
+    torch.manual_seed(3)
+    d, n, B, M = 64, 256, 320, 2
+    sig = S.FunctionalTiedSAE if kind == "tied" else S.FunctionalSAE
+    models = []
+    for a in (1e-3, 1e-2):
+        p, b = sig.init(d, n, a) if kind == "tied" else sig.init(d, n, a, bias_decay=0.01)
+        p["encoder_bias"] = 0.02 * torch.randn(n)
+        models.append((p, b))
+    ens = S.FunctionalEnsemble([({k: v.clone() for k, v in p.items()}, {k: v.clone() for k, v in b.items()})
+                                for p, b in models], sig, S.adam, {"lr": 1e-3}, device="cuda", arith="f16f8")
+    gen = torch.Generator().manual_seed(4)
+    for step, exact in enumerate([True, False, True, True, False]):
+        X = torch.randn(B, d, generator=gen)
+        if exact:
+            X = X.half().float()
+        grads, (loss, aux) = ens.grads_batch(X.cuda())
+        code = aux["c"].dense().cpu()
+        for i, (p, b) in enumerate(models):
+            pd = {k: v.double() for k, v in p.items()}
+            if kind == "tied":
+                f, _ = tied_grads_engine_kinks(p, b, X, code[i])
+            else:
+                f = O.untied_grads(pd["encoder"], pd["encoder_bias"], pd["decoder"], X.double(), float(b["l1_alpha"]),
+                                   float(b["bias_decay"]))
+            assert abs(float(loss["loss"][i]) - float(f["loss"])) <= REL * abs(float(f["loss"])), (step, exact, i)
+            assert relnorm(code[i], f["c"]) <= REL, (step, exact, i)
+            if kind == "tied":
+                assert relnorm(grads["encoder"][i], f["grads"]["encoder"]) <= 2e-4, (step, exact, i)
+                assert relnorm(grads["encoder_bias"][i], f["grads"]["encoder_bias"]) <= 2e-4, (step, exact, i)
+
+
 @pytest.mark.parametrize("arith", ARITHS)
 @pytest.mark.parametrize("mode", ["frozen_t1", "standard"])
 @pytest.mark.parametrize("kind", ["tied", "untied"])
