@@ -53,13 +53,18 @@ struct GemmParams {
   int passes;     // 3: hi*hi + hi*lo + lo*hi (f16f8: fp16 hh + two fp8 cross terms), 1: hi*hi
   int n_models, m_total, n_total;
   int tiles_m, tiles_n;
+  // NSUB == 2 only: the last `tail_rows` row blocks (model-major order) are processed as single-width tiles, two per
+  // row block, so that the final wave of the persistent grid is not half empty (requires tiles_n == 1). 0 = none.
+  int tail_rows;
   EpiParams epi;
 };
 
-template <int BN, int BK, bool A_MN, bool B_MN, int STAGES, int EPI_WARP_BYTES = 0, bool CTA2 = false, int ARITH = 0>
+template <int BN, int BK, bool A_MN, bool B_MN, int STAGES, int EPI_WARP_BYTES = 0, bool CTA2 = false, int ARITH = 0,
+          int NSUB = 1>
 struct GemmSmem {
   static constexpr int kATile = kBM * BK * 2;   // bytes, one of hi/lo
-  static constexpr int kBRows = CTA2 ? BN / 2 : BN;  // a CTA pair splits the B tile between its two CTAs
+  static constexpr int kBSub = CTA2 ? BN / 2 : BN;   // B rows of ONE sub-tile held by this CTA (a pair splits B)
+  static constexpr int kBRows = NSUB * kBSub;        // NSUB sub-tiles of BN output columns share one A tile
   static constexpr int kBTile = kBRows * BK * 2;
   // bf16x3: hi and lo planes of A and B. f16f8: either the fp16 planes or the four 8-bit planes (same bytes).
   static constexpr int kStage = ARITH == 1 ? kATile + kBTile : 2 * kATile + 2 * kBTile;
@@ -91,23 +96,30 @@ struct GemmSmem {
 // products is as short as with SPLIT_ACC.
 constexpr int kArithBf16x3 = 0, kArithF16F8 = 1;
 
+//
+// NSUB = 2 (f16f8 only): the output tile is 256 x (2 * BN): both BN-column halves are accumulated from ONE A tile per
+// K block (two MMAs per K slice, two accumulators filling all 512 TMEM columns, so no accumulator double-buffering —
+// for GEMMs whose epilogue is negligible). Shared memory then takes 96 instead of 128 KB per two tiles' worth of MMAs
+// (the f16f8 main loop otherwise runs exactly at the SM's shared-memory bandwidth), and the A operand is read from
+// L2 / HBM once instead of once per column half.
 template <class Epi, int BN, int BK, bool A_MN, bool B_MN, int STAGES, bool SPLIT_ACC = false, bool CTA2 = false,
-          int ARITH = kArithBf16x3>
+          int ARITH = kArithBf16x3, int NSUB = 1>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_split_kernel(const __grid_constant__ GemmParams<typename Epi::Params> p) {
   constexpr bool F8 = ARITH == kArithF16F8;
+  static_assert(NSUB == 1 || (NSUB == 2 && F8 && BN == 256), "two sub-tiles: f16f8, 256 columns each");
   static_assert(!F8 || !SPLIT_ACC, "f16f8 rescales in the accumulator; no split accumulators");
   static_assert(!F8 || BK % 32 == 0, "an fp8 instruction covers K = 32");
   static_assert(BN % 64 == 0 && BN <= 256, "BN must be a multiple of 64, at most 256");
   static_assert(BK % 16 == 0 && BK <= 64, "BK in {16,32,48,64}");
   static_assert(A_MN || BK == 64 || BK == 32, "K-major A: one swizzled row per tile row, 128 B (BK=64) or 64 B (BK=32)");
   static_assert(B_MN || BK == 64 || BK == 32, "K-major B: one swizzled row per tile row, 128 B (BK=64) or 64 B (BK=32)");
-  using SM = GemmSmem<BN, BK, A_MN, B_MN, STAGES, Epi::kWarpStageBytes, CTA2, ARITH>;
+  using SM = GemmSmem<BN, BK, A_MN, B_MN, STAGES, Epi::kWarpStageBytes, CTA2, ARITH, NSUB>;
   static_assert(!CTA2 || BN % 128 == 0, "a CTA pair splits B in halves of whole 64-column boxes");
   constexpr int EC = Epi::kCols;  // accumulator columns handed to the epilogue per call (32 or 64)
   static_assert(EC == 32 || EC == 64, "epilogue chunk is 32 or 64 columns");
   static_assert(BN % EC == 0, "tile width must be a multiple of the epilogue chunk");
-  constexpr int kAccStages = SPLIT_ACC ? 1 : 2;
+  constexpr int kAccStages = (SPLIT_ACC || NSUB == 2) ? 1 : 2;
   constexpr uint32_t kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
                                  : (2 * BN <= 256) ? 256 : 512;
 
@@ -125,7 +137,25 @@ gemm_split_kernel(const __grid_constant__ GemmParams<typename Epi::Params> p) {
   const int cta_rank = CTA2 ? int(cluster_ctarank()) : 0;
   const int tile0 = CTA2 ? int(blockIdx.x >> 1) : int(blockIdx.x);       // first tile of this CTA (pair)
   const int tile_step = CTA2 ? int(gridDim.x >> 1) : int(gridDim.x);
-  const int num_tiles = p.n_models * p.tiles_m * p.tiles_n;
+  const int big_tiles = (p.n_models * p.tiles_m - (NSUB == 2 ? p.tail_rows : 0)) * p.tiles_n;
+  const int num_tiles = big_tiles + (NSUB == 2 ? 2 * p.tail_rows : 0);
+  // tile index -> (model, tile row, first BN-column block, number of BN-column sub-tiles)
+  auto decode_tile = [&](int tile, int& model, int& tile_m, int& n0, int& nsub) {
+    if (NSUB == 2 && tile >= big_tiles) {
+      const int t = tile - big_tiles;
+      const int rb = big_tiles + (t >> 1);   // tiles_n == 1 here: row block index == big tile index
+      model = rb / p.tiles_m;
+      tile_m = rb - model * p.tiles_m;
+      n0 = t & 1;
+      nsub = 1;
+    } else {
+      model = tile / (p.tiles_m * p.tiles_n);
+      const int rem = tile - model * (p.tiles_m * p.tiles_n);
+      tile_m = rem / p.tiles_n;
+      n0 = (rem % p.tiles_n) * NSUB;
+      nsub = NSUB;
+    }
+  };
   const int kblocks = (p.k_total + BK - 1) / BK;
   const bool three = p.passes >= 3;
 
@@ -181,21 +211,23 @@ gemm_split_kernel(const __grid_constant__ GemmParams<typename Epi::Params> p) {
   if (warp == 0) {
     // ======================= TMA producer =======================
     if (lane == 0) {
-      const uint32_t stage_bytes = (three && !F8) ? uint32_t(SM::kStage) : uint32_t(SM::kATile + SM::kBTile);
+      const uint32_t stage_bytes_full = (three && !F8) ? uint32_t(SM::kStage) : uint32_t(SM::kATile + SM::kBTile);
       // one copy: same-CTA barrier, or (pair) the cta_group::2 form that completes on CTA 0's barrier
       auto load = [&](void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
         if constexpr (CTA2) tma_load_3d_2cta(dst, m, bar, c0, c1, c2);
         else tma_load_3d(dst, m, bar, c0, c1, c2);
       };
-      constexpr int kBHalf = SM::kBRows;  // B rows (N index) this CTA loads
+      constexpr int kBHalf = SM::kBSub;  // B rows (N index) of one sub-tile this CTA loads
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = tile0; tile < num_tiles; tile += tile_step) {
-        const int model = tile / (p.tiles_m * p.tiles_n);
-        const int rem = tile - model * (p.tiles_m * p.tiles_n);
-        const int m_blk = (rem / p.tiles_n) * (CTA2 ? 2 : 1) + cta_rank;
-        const int n_blk = rem % p.tiles_n;
-        const int b_row0 = n_blk * BN + cta_rank * kBHalf;
+        int model, tile_m, n0, nsub;
+        decode_tile(tile, model, tile_m, n0, nsub);
+        const int m_blk = tile_m * (CTA2 ? 2 : 1) + cta_rank;
+        const int b_row0 = n0 * BN + cta_rank * kBHalf;  // (+ sub * BN for the second sub-tile)
+        [[maybe_unused]] const int n_blk = n0;
+        // bytes of a 16-bit stage of THIS tile (a tail tile of an NSUB = 2 launch loads one sub-tile of B only)
+        const uint32_t stage_bytes = F8 ? uint32_t(SM::kATile + nsub * (SM::kBSub * BK * 2)) : stage_bytes_full;
         if constexpr (F8) {
           // sweep 1: the 8-bit planes (skipped for passes == 1); sweep 2: the fp16 planes
           for (int sweep = three ? 0 : 1; sweep < 2; ++sweep)
@@ -220,11 +252,15 @@ gemm_split_kernel(const __grid_constant__ GemmParams<typename Epi::Params> p) {
                     for (int j = 0; j < kBM / 64; ++j)
                       load(sa + j * (BK * 128), &p.a_hi[set], &full_bar[stage], m_blk * kBM + j * 64, k0, am);
                   }
-                  if constexpr (!B_MN) load(sb, &p.b_hi[set], &full_bar[stage], k0, b_row0, bm);
-                  else {
+                  for (int sub = 0; sub < nsub; ++sub) {
+                    uint8_t* sbs = sb + sub * (kBHalf * BK * 2);
+                    const int r0 = b_row0 + sub * BN;
+                    if constexpr (!B_MN) load(sbs, &p.b_hi[set], &full_bar[stage], k0, r0, bm);
+                    else {
 #pragma unroll
-                    for (int j = 0; j < kBHalf / 64; ++j)
-                      load(sb + j * (BK * 128), &p.b_hi[set], &full_bar[stage], b_row0 + j * 64, k0, bm);
+                      for (int j = 0; j < kBHalf / 64; ++j)
+                        load(sbs + j * (BK * 128), &p.b_hi[set], &full_bar[stage], r0 + j * 64, k0, bm);
+                    }
                   }
                 } else {
                   uint8_t* sa_h = st;
@@ -239,15 +275,20 @@ gemm_split_kernel(const __grid_constant__ GemmParams<typename Epi::Params> p) {
                     if (t_hl) load(sa_h, &p.a_lo[set], &full_bar[stage], m_blk * kBM, k0, am);
                     if (t_lh) load(sa_l, &p.a_x8[set], &full_bar[stage], m_blk * kBM, k0, am);
                   }
-                  if constexpr (!B_MN) {
-                    if (t_lh) load(sb_h, &p.b_lo[set], &full_bar[stage], k0, b_row0, bm);
-                    if (t_hl) load(sb_l, &p.b_x8[set], &full_bar[stage], k0, b_row0, bm);
-                  } else {
-                    static_assert(!F8 || !B_MN || kBHalf % 128 == 0, "MN-major 8-bit B tiles come in 128-element boxes");
+                  for (int sub = 0; sub < nsub; ++sub) {
+                    uint8_t* sbh = sb_h + sub * (kBHalf * BK);
+                    uint8_t* sbl = sb_l + sub * (kBHalf * BK);
+                    const int r0 = b_row0 + sub * BN;
+                    if constexpr (!B_MN) {
+                      if (t_lh) load(sbh, &p.b_lo[set], &full_bar[stage], k0, r0, bm);
+                      if (t_hl) load(sbl, &p.b_x8[set], &full_bar[stage], k0, r0, bm);
+                    } else {
+                      static_assert(!F8 || !B_MN || kBHalf % 128 == 0, "MN-major 8-bit B tiles come in 128-element boxes");
 #pragma unroll
-                    for (int j = 0; j < kBHalf / 128; ++j) {
-                      if (t_lh) load(sb_h + j * (BK * 128), &p.b_lo[set], &full_bar[stage], b_row0 + j * 128, k0, bm);
-                      if (t_hl) load(sb_l + j * (BK * 128), &p.b_x8[set], &full_bar[stage], b_row0 + j * 128, k0, bm);
+                      for (int j = 0; j < kBHalf / 128; ++j) {
+                        if (t_lh) load(sbh + j * (BK * 128), &p.b_lo[set], &full_bar[stage], r0 + j * 128, k0, bm);
+                        if (t_hl) load(sbl + j * (BK * 128), &p.b_x8[set], &full_bar[stage], r0 + j * 128, k0, bm);
+                      }
                     }
                   }
                 }
@@ -327,9 +368,11 @@ gemm_split_kernel(const __grid_constant__ GemmParams<typename Epi::Params> p) {
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+        int nsub = NSUB;
+        if constexpr (NSUB == 2) nsub = tile >= big_tiles ? 1 : 2;
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + uint32_t(acc * BN);
+        const uint32_t d_tmem = tmem_base + uint32_t(acc * BN);   // (NSUB == 2: one stage, sub-tile s at column s * BN)
         const uint32_t d_cross = SPLIT_ACC ? tmem_base + uint32_t(BN) : d_tmem;
         uint32_t accumulate = 0;
         if constexpr (F8) {
@@ -355,16 +398,23 @@ gemm_split_kernel(const __grid_constant__ GemmParams<typename Epi::Params> p) {
               for (int k = 0; k < BK / 32; ++k) {
                 const uint64_t ah = make_sdesc(sa_h + k * a8_kstep, a_lbo, a8_sbo, a8_lt);
                 const uint64_t al = make_sdesc(sa_l + k * a8_kstep, a_lbo, a8_sbo, a8_lt);
-                const uint64_t bh = make_sdesc(sb_h + k * b8_kstep, b_lbo, b8_sbo, b8_lt);
-                const uint64_t bl = make_sdesc(sb_l + k * b8_kstep, b_lbo, b8_sbo, b8_lt);
-                if (t_lh) {
-                  umma_f8<CTA2>(d_tmem, al, bh, i8, accumulate);
-                  accumulate = 1;
+                uint32_t acc_after = accumulate;
+                for (int sub = 0; sub < nsub; ++sub) {
+                  const uint32_t sub8 = uint32_t(sub * (SM::kBSub * BK));   // bytes of one sub-tile's 8-bit plane
+                  const uint64_t bh = make_sdesc(sb_h + sub8 + k * b8_kstep, b_lbo, b8_sbo, b8_lt);
+                  const uint64_t bl = make_sdesc(sb_l + sub8 + k * b8_kstep, b_lbo, b8_sbo, b8_lt);
+                  uint32_t acc_s = accumulate;
+                  if (t_lh) {
+                    umma_f8<CTA2>(d_tmem + uint32_t(sub * BN), al, bh, i8, acc_s);
+                    acc_s = 1;
+                  }
+                  if (t_hl) {
+                    umma_f8<CTA2>(d_tmem + uint32_t(sub * BN), ah, bl, i8, acc_s);
+                    acc_s = 1;
+                  }
+                  acc_after = acc_s;
                 }
-                if (t_hl) {
-                  umma_f8<CTA2>(d_tmem, ah, bl, i8, accumulate);
-                  accumulate = 1;
-                }
+                accumulate = acc_after;
               }
               commit(&empty_bar[stage]);
               if (++stage == STAGES) {
@@ -383,13 +433,12 @@ gemm_split_kernel(const __grid_constant__ GemmParams<typename Epi::Params> p) {
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k) {
               const uint64_t ah = make_sdesc(sa + k * a_kstep, a_lbo, a_sbo, a_lt);
-              const uint64_t bh = make_sdesc(sb + k * b_kstep, b_lbo, b_sbo, b_lt);
-              if (k == 0 && rescale) {
-                umma_f16_rescale<CTA2>(d_tmem, ah, bh, i16);  // D = ah*bh + D * 2^-kLoShift
-                rescale = false;
-              } else {
-                mma16(d_tmem, ah, bh, i16, accumulate);
+              for (int sub = 0; sub < nsub; ++sub) {
+                const uint64_t bh = make_sdesc(sb + uint32_t(sub * (SM::kBSub * BK * 2)) + k * b_kstep, b_lbo, b_sbo, b_lt);
+                if (k == 0 && rescale) umma_f16_rescale<CTA2>(d_tmem + uint32_t(sub * BN), ah, bh, i16);  // D = ah*bh + D * 2^-kLoShift
+                else mma16(d_tmem + uint32_t(sub * BN), ah, bh, i16, accumulate);
               }
+              if (k == 0) rescale = false;
               accumulate = 1;
             }
             commit(&empty_bar[stage]);
@@ -444,20 +493,22 @@ gemm_split_kernel(const __grid_constant__ GemmParams<typename Epi::Params> p) {
     uint32_t acc_phase = 0;
     for (int tile = tile0; tile < num_tiles; tile += tile_step) {
       TileCoord tc;
-      tc.model = tile / (p.tiles_m * p.tiles_n);
-      const int rem = tile - tc.model * (p.tiles_m * p.tiles_n);
-      tc.m_blk = (rem / p.tiles_n) * (CTA2 ? 2 : 1) + cta_rank;
-      tc.n_blk = rem % p.tiles_n;
+      int tile_m, n0, nsub;
+      decode_tile(tile, tc.model, tile_m, n0, nsub);
+      tc.m_blk = tile_m * (CTA2 ? 2 : 1) + cta_rank;
       tc.row = tc.m_blk * kBM + wq * 32 + lane;
-      tc.col0 = tc.n_blk * BN;
       tc.warp_q = wq;
       tc.grp = grp;
       tc.lane = lane;
-      Epi epi(p.epi, tc, p.m_total, p.n_total, smem + SM::kEpiOff + (grp * 4 + wq) * Epi::kWarpStageBytes);
 
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + uint32_t(acc * BN) + (uint32_t(wq * 32) << 16);
+#pragma unroll 1
+      for (int sub = 0; sub < nsub; ++sub) {
+      tc.n_blk = n0 + sub;   // in units of BN columns
+      tc.col0 = tc.n_blk * BN;
+      Epi epi(p.epi, tc, p.m_total, p.n_total, smem + SM::kEpiOff + (grp * 4 + wq) * Epi::kWarpStageBytes);
+      const uint32_t taddr = tmem_base + uint32_t((acc * NSUB + sub) * BN) + (uint32_t(wq * 32) << 16);
       constexpr int kChunks = BN / EC;
       static_assert(kChunks % 2 == 0, "the two epilogue warp groups alternate chunks");
 #pragma unroll 1
@@ -476,7 +527,7 @@ gemm_split_kernel(const __grid_constant__ GemmParams<typename Epi::Params> p) {
           }
         }
         tmem_ld_wait();
-        if (c + 2 >= kChunks) {
+        if (c + 2 >= kChunks && sub == nsub - 1) {
           // all TMEM reads of this accumulator are done: hand it back to the MMA warp early
           tc_fence_before();
           __syncwarp();
@@ -488,6 +539,7 @@ gemm_split_kernel(const __grid_constant__ GemmParams<typename Epi::Params> p) {
         epi.chunk(c * EC, r);
       }
       epi.finish();
+      }
       if (++acc == kAccStages) {
         acc = 0;
         acc_phase ^= 1;

@@ -293,9 +293,10 @@ static bool tmaps_f8(const OperandF8& o, uint32_t box_rows_kmajor, int BK, CUten
          make_tmap_u8_box(l8, o.d_l8, o.models, o.K, o.rows, o.pitch, mp, 128, BK, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
-template <int BN, int BK, bool A_MN, bool B_MN, int STAGES, bool CTA2>
+template <int BN, int BK, bool A_MN, bool B_MN, int STAGES, bool CTA2, int NSUB = 1>
 static bool run_case_f8(const char* name, int models, int M, int N, int K, int nsets, int passes, bool a_shared,
-                        bool b_shared, int reps = 1, int exact = 0 /*1: A of set 0, 2: B of set 0 is fp16-exact + flagged*/) {
+                        bool b_shared, int reps = 1, int exact = 0 /*1: A of set 0, 2: B of set 0 is fp16-exact + flagged*/,
+                        int tail_rows = 0 /*NSUB == 2: trailing row blocks run as single-width tiles*/) {
   OperandF8 A[2], B[2];
   for (int s = 0; s < nsets; ++s) {
     make_operand_f8(A[s], a_shared ? 1 : models, M, K, A_MN, 3.0f, s == 0 && exact == 1);
@@ -319,19 +320,20 @@ static bool run_case_f8(const char* name, int models, int M, int N, int K, int n
     p.a_batched[s] = a_shared ? 0 : 1;
     p.b_batched[s] = b_shared ? 0 : 1;
   }
+  if (NSUB == 2 && tail_rows > 0) p.tail_rows = tail_rows;   // (requires N <= 2 * BN; see GemmParams::tail_rows)
   if (exact == 1) p.a_res_flag[0] = d_flag;
   if (exact == 2) p.b_res_flag[0] = d_flag;
   p.nsets = nsets; p.k_total = K; p.passes = passes; p.n_models = models; p.m_total = M; p.n_total = N;
   const int tile_rows = CTA2 ? 2 * kBM : kBM;
   p.tiles_m = (M + tile_rows - 1) / tile_rows;
-  p.tiles_n = (N + BN - 1) / BN;
+  p.tiles_n = (N + NSUB * BN - 1) / (NSUB * BN);
   p.epi.out = d_out; p.epi.model_stride = (long long)M * N; p.epi.ld = N;
-  using SM = GemmSmem<BN, BK, A_MN, B_MN, STAGES, 0, CTA2, kArithF16F8>;
-  auto kern = gemm_split_kernel<EpiStoreF32, BN, BK, A_MN, B_MN, STAGES, false, CTA2, kArithF16F8>;
+  using SM = GemmSmem<BN, BK, A_MN, B_MN, STAGES, 0, CTA2, kArithF16F8, NSUB>;
+  auto kern = gemm_split_kernel<EpiStoreF32, BN, BK, A_MN, B_MN, STAGES, false, CTA2, kArithF16F8, NSUB>;
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kBytes));
   int sms = 0;
   CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
-  int tiles = models * p.tiles_m * p.tiles_n;
+  int tiles = models * p.tiles_m * p.tiles_n + p.tail_rows;
   const int units = CTA2 ? sms / 2 : sms;
   int grid = (tiles < units ? tiles : units) * (CTA2 ? 2 : 1);
   cudaEvent_t e0, e1;
@@ -442,6 +444,16 @@ int main(int argc, char** argv) {
     ok &= run_case_f8<256, 64, false, false, 4, false>("f8_kk_exactA", 2, 200, 328, 104, 1, 3, true, false, 1, 1);
     ok &= run_case_f8<256, 64, true, true, 6, true>("f8_pair_mnmn_exactB", 2, 512, 512, 320, 2, 3, false, true, 1, 2);
     ok &= run_case_f8<256, 64, true, true, 4, false>("f8_mnmn_exactB", 2, 200, 328, 104, 2, 3, false, true, 1, 2);
+    // two 256-column sub-tiles per A tile (weight-gradient shape, CTA pairs)
+    ok &= run_case_f8<256, 64, true, true, 4, true, 2>("f8_nsub2_mnmn_2set", 2, 512, 512, 320, 2, 3, false, true);
+    ok &= run_case_f8<256, 64, true, true, 4, true, 2>("f8_nsub2_mnmn_wide", 2, 768, 1024, 320, 2, 3, false, true);
+    ok &= run_case_f8<256, 64, true, true, 4, true, 2>("f8_nsub2_mnmn_ragged", 2, 200, 328, 104, 2, 3, false, true);
+    ok &= run_case_f8<256, 64, true, true, 4, true, 2>("f8_nsub2_mnmn_exactB", 2, 512, 512, 320, 2, 3, false, true, 1, 2);
+    ok &= run_case_f8<256, 64, false, false, 4, true, 2>("f8_nsub2_kk", 3, 768, 512, 512, 1, 3, true, false);
+    // ... with the last row blocks as single-width tail tiles (3 models x 3 row blocks = 9 row blocks, 4 of them tail)
+    ok &= run_case_f8<256, 64, true, true, 4, true, 2>("f8_nsub2_tail", 3, 768, 512, 320, 2, 3, false, true, 1, 0, 4);
+    ok &= run_case_f8<256, 64, true, true, 4, true, 2>("f8_nsub2_tail_ragged", 2, 200, 328, 104, 2, 3, false, true, 1, 2, 1);
+    ok &= run_case_f8<256, 64, true, true, 4, true, 2>("f8_nsub2_tail_all", 2, 512, 512, 320, 2, 3, false, true, 1, 0, 4);
     }
     if (f8big) {
       // same-box comparison: the bf16x3 kernels the engine uses today (3 passes) at config-2 shapes
@@ -455,6 +467,8 @@ int main(int argc, char** argv) {
       ok &= run_case_f8<256, 64, false, false, 6, true>("f8_big_enc_hh", 4, 8192, 4096, 512, 1, 1, true, false, 10);
       ok &= run_case_f8<256, 64, false, false, 6, true>("f8_big_encode_exactA", 4, 8192, 4096, 512, 1, 3, true, false, 10, 1);
       ok &= run_case_f8<256, 64, true, true, 6, true>("f8_big_dw_exactB", 4, 4096, 512, 8192, 2, 3, false, true, 10, 2);
+      ok &= run_case_f8<256, 64, true, true, 4, true, 2>("f8_big_dw_nsub2", 4, 4096, 512, 8192, 2, 3, false, true, 10);
+      ok &= run_case_f8<256, 64, true, true, 4, true, 2>("f8_big_dw_nsub2_exactB", 4, 4096, 512, 8192, 2, 3, false, true, 10, 2);
     }
     if (f8only || f8big) {
       printf(ok ? "ALL PASS\n" : "SOME FAILED\n");
