@@ -167,6 +167,12 @@ int sce_set_step_count(sce_plan* plan, long long steps_taken);
 /* Number of kernels the most recent sce_step / sce_forward on this plan launched. */
 int sce_last_launch_count(const sce_plan* plan);
 
+/* F16F8 plans: the largest |x| over every batch fed since the last sce_prepare (NaN if a batch held one), read back
+ * with one 4-byte copy and a stream synchronise — a monitor for the fp16 range the arithmetic assumes (values beyond
+ * 65504 become inf/NaN in the losses, magnitudes far below 1e-3 lose relative precision: use SCE_ARITH_BF16X3 for
+ * such data). BF16X3 plans report 0. */
+int sce_input_absmax(sce_plan* plan, float* out_host, void* stream);
+
 /* The arithmetic the plan resolved to: SCE_ARITH_BF16X3 or SCE_ARITH_F16F8. */
 int sce_plan_arith(const sce_plan* plan);
 

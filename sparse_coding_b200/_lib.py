@@ -24,7 +24,7 @@ EXPORTS = [
     "sce_version", "sce_last_error", "sce_workspace_bytes", "sce_plan_create", "sce_plan_destroy", "sce_prepare",
     "sce_step", "sce_step_host", "sce_forward", "sce_read_code", "sce_grads", "sce_gather_rows",
     "sce_last_launch_count", "sce_get_step_count", "sce_set_step_count", "sce_profile_begin", "sce_profile_end",
-    "sce_plan_arith",
+    "sce_plan_arith", "sce_input_absmax",
 ]
 PHASES = ["split", "encode", "decode", "losses", "dcode", "dw", "adam"]
 
@@ -87,6 +87,7 @@ def load():
     lib.sce_profile_begin.argtypes = [vp]
     lib.sce_profile_end.argtypes = [vp, vp, vp]
     lib.sce_plan_arith.argtypes = [vp]
+    lib.sce_input_absmax.argtypes = [vp, vp, vp]
     for name in EXPORTS:
         getattr(lib, name)  # AttributeError here means header and library disagree
     _lib = lib

@@ -805,6 +805,7 @@ int sce_plan_destroy(sce_plan* plan) {
 int sce_prepare(sce_plan* p, void* stream) {
   if (!p) return fail(SCE_ERR_INVALID, "plan is NULL");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CUDA_TRY(cudaMemsetAsync(p->res_flags, 0, 8 * sizeof(uint32_t), st));   // residual flag + input range monitor
   const sce_desc& d = p->d;
   const long long rows = (long long)d.n_models * d.n;
   AdamHyper h = hyper_for(p, 1);
@@ -1012,6 +1013,17 @@ int sce_gather_rows(const void* chunk, int chunk_is_half, long long n_rows, int 
 }
 
 int sce_last_launch_count(const sce_plan* plan) { return plan ? plan->last_launches : 0; }
+int sce_input_absmax(sce_plan* plan, float* out_host, void* stream) {
+  if (!plan || !out_host) return fail(SCE_ERR_INVALID, "plan / out_host is NULL");
+  *out_host = 0.f;
+  if (plan->arith != kArithF16F8) return SCE_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint32_t bits = 0;
+  CUDA_TRY(cudaMemcpyAsync(&bits, plan->res_flags + 1, sizeof(bits), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  memcpy(out_host, &bits, sizeof(bits));
+  return SCE_OK;
+}
 int sce_plan_arith(const sce_plan* plan) {
   return !plan ? 0 : plan->arith == kArithF16F8 ? SCE_ARITH_F16F8 : SCE_ARITH_BF16X3;
 }

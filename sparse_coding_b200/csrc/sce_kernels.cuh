@@ -33,15 +33,19 @@ __device__ __forceinline__ void store_planes4(const float (&v)[4], void* hi, voi
 
 // f16f8: `res_flag` (zeroed by the caller) is set to 1 when any element has a non-zero residual plane entry, i.e. is
 // not exactly representable in fp16; the GEMMs that read x skip the corresponding cross term while it stays 0.
+// res_flag[1] accumulates the bit pattern of the largest |x| seen since the plan was created (a monitor for the
+// fp16 range this arithmetic assumes; sce_input_absmax reads it).
 template <int ARITH>
 __global__ void split_rows_kernel(const float* __restrict__ x, void* __restrict__ hi, void* __restrict__ lo,
                                   void* __restrict__ x8, long long n4, uint32_t* __restrict__ res_flag) {
   const long long stride = (long long)gridDim.x * blockDim.x;
   uint32_t any = 0;
+  float amax = 0.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
     const float4 v = reinterpret_cast<const float4*>(x)[i];
     const float vv[4] = {v.x, v.y, v.z, v.w};
     if constexpr (ARITH == kArithF16F8) {
+      amax = fmaxf(fmaxf(amax, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
       uint2 h16;
       uint32_t h8, l8;
       split4_f16f8(vv, h16, h8, l8);
@@ -55,6 +59,12 @@ __global__ void split_rows_kernel(const float* __restrict__ x, void* __restrict_
   }
   if constexpr (ARITH == kArithF16F8) {
     if (res_flag && __any_sync(0xffffffffu, any != 0u) && (threadIdx.x & 31) == 0) *res_flag = 1u;  // benign race: all write 1
+    if (res_flag) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+      // non-negative floats order like their bit patterns (a NaN input has the largest pattern and sticks)
+      if ((threadIdx.x & 31) == 0 && __float_as_uint(amax) > res_flag[1]) atomicMax(res_flag + 1, __float_as_uint(amax));
+    }
   }
 }
 

@@ -427,6 +427,18 @@ class FunctionalEnsemble:
             return None
         return _lib.ARITH_NAME.get(int(_lib.load().sce_plan_arith(self._plan)))
 
+    def input_absmax(self) -> float:
+        """f16f8 plans: the largest |x| the engine has been fed since the plan was (re)prepared (one 4-byte D2H copy +
+        stream sync; 0.0 for bf16x3 / before the first step). Values beyond 65504 overflow the fp16 operand plane
+        (losses turn inf/NaN), magnitudes far below 1e-3 lose relative precision: switch such data to
+        ``arith="bf16x3"``. ``ensemble_train_loop`` checks this once per chunk."""
+        if self._plan is None:
+            return 0.0
+        out = C.c_float(0.0)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().sce_input_absmax(self._plan, C.byref(out), self._stream()), "sce_input_absmax")
+        return float(out.value)
+
     def unstack(self, device=None):
         params = unstack_dict(self.params, self.n_models, device=device)
         buffers = unstack_dict(self.buffers, self.n_models, device=device)

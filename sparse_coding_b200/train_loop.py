@@ -124,6 +124,18 @@ def ensemble_train_loop(ensemble, cfg, args, ensemble_name, sampler, dataset, pr
                 log[f"{ensemble_name}_{name}_num_nonzero"] = nnz_host[m].item()
             run.log(log, commit=True)
         progress_counter.value = i
+    check_input_range(ensemble)
+
+
+def check_input_range(ensemble) -> None:
+    """Once per chunk (one 4-byte D2H copy): warn when the activations fed to an f16f8 plan leave the range its fp16
+    operand plane holds well (include/sce.h, sce_arith) — the losses would already show inf/NaN for an overflow;
+    very small magnitudes only cost precision, silently."""
+    amax = ensemble.input_absmax() if hasattr(ensemble, "input_absmax") else 0.0
+    if amax != amax or amax > 3.0e4 or 0.0 < amax < 1.0e-3:
+        import warnings
+        warnings.warn(f"largest |activation| fed to the f16f8 arithmetic so far is {amax:g}: outside [1e-3, 3e4]; "
+                      "construct the FunctionalEnsemble with arith='bf16x3' (fp32 range) for this data", RuntimeWarning)
 
 
 def unstacked_to_learned_dicts(ensemble, args, ensemble_hyperparams, buffer_hyperparams):

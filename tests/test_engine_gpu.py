@@ -201,6 +201,27 @@ def test_exact_zero_rows_clamp_gradient():
     assert int(aux["c"].dense()[0, 5].count_nonzero()) == 0
 
 
+def test_input_range_monitor():
+    """sce_input_absmax: the running maximum of |x| an f16f8 plan has been fed (train_loop warns outside [1e-3, 3e4])."""
+    import sparse_coding_b200 as S
+    torch.manual_seed(0)
+    models = [S.FunctionalTiedSAE.init(32, 64, 1e-3)]
+    ens = S.FunctionalEnsemble(models, S.FunctionalTiedSAE, S.adam, {"lr": 1e-3}, device="cuda", arith="f16f8")
+    assert ens.input_absmax() == 0.0
+    X = torch.randn(40, 32)
+    ens.step_batch(X.cuda())
+    assert ens.input_absmax() == float(X.abs().max())
+    Y = 0.5 * torch.randn(24, 32)
+    Y[3, 7] = -123.5
+    ens.step_batch(Y.cuda())
+    assert ens.input_absmax() == 123.5
+    ens.step_batch(X.cuda())
+    assert ens.input_absmax() == 123.5
+    ref = S.FunctionalEnsemble(models, S.FunctionalTiedSAE, S.adam, {"lr": 1e-3}, device="cuda", arith="bf16x3")
+    ref.step_batch(X.cuda())
+    assert ref.input_absmax() == 0.0
+
+
 @pytest.mark.parametrize("kind", ["tied", "untied"])
 def test_fp16_exact_batches_skip_the_residual_term(kind):
     """Activation chunks are fp16 on disk (activation_dataset.py:404-412): such a batch has an all-zero residual
