@@ -421,7 +421,8 @@ def main():
         if tr:
             line["roofline"]["traffic"] = tr["dw_dram_bytes_per_launch"]
             line["roofline"]["traffic_source"] = tr["source"]
-            line["roofline"]["alg_bytes_per_launch"] = 2 * 4.0 * M * B * n + 4.0 * M * n * d   # dz,c (hi,lo) + dW
+            # dz and c at 4 B / element (3 B for dz when x's residual term is skipped: its h8 plane is not read) + dW
+            line["roofline"]["alg_bytes_per_launch"] = (8.0 - (1.0 if x_skip else 0.0)) * M * B * n + 4.0 * M * n * d
         if ms_alt == ms_alt:
             line["alt_precision"] = {"note": "informational only: backward GEMMs on the 16-bit plane alone (bwd_passes=1); "
                                              "forward, losses and x̂ unchanged",

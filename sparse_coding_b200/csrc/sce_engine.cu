@@ -183,7 +183,7 @@ static size_t carve(sce_plan* p, const sce_desc& d, uint8_t* base) {
   auto lob = c.take<float>(M);
   auto ls = c.take<float>(M * 4);
   auto ns = c.take<float>(M);
-  auto rf = c.take<uint32_t>(8);
+  auto rf = c.take<uint32_t>(64);   // [0] residual flag, [kAbsmaxWord] input range monitor (separate 128-byte lines)
   if (p) {
     p->x_stage = X;
     p->x_hi = xh;
@@ -805,7 +805,7 @@ int sce_plan_destroy(sce_plan* plan) {
 int sce_prepare(sce_plan* p, void* stream) {
   if (!p) return fail(SCE_ERR_INVALID, "plan is NULL");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  CUDA_TRY(cudaMemsetAsync(p->res_flags, 0, 8 * sizeof(uint32_t), st));   // residual flag + input range monitor
+  CUDA_TRY(cudaMemsetAsync(p->res_flags, 0, 64 * sizeof(uint32_t), st));   // residual flag + input range monitor
   const sce_desc& d = p->d;
   const long long rows = (long long)d.n_models * d.n;
   AdamHyper h = hyper_for(p, 1);
@@ -1019,7 +1019,7 @@ int sce_input_absmax(sce_plan* plan, float* out_host, void* stream) {
   if (plan->arith != kArithF16F8) return SCE_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   uint32_t bits = 0;
-  CUDA_TRY(cudaMemcpyAsync(&bits, plan->res_flags + 1, sizeof(bits), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(&bits, plan->res_flags + kAbsmaxWord, sizeof(bits), cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
   memcpy(out_host, &bits, sizeof(bits));
   return SCE_OK;
