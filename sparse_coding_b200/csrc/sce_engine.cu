@@ -72,6 +72,7 @@ struct sce_plan {
   __nv_bfloat16 *g_hi, *g_lo;     // [M, Bmax, d]
   __nv_bfloat16 *dz_hi, *dz_lo;   // [M, Bmax, n]   (top-k: fp32 scores alias these planes)
   uint8_t *x_x8, *wenc_x8, *wdec_x8, *c_x8, *g_x8, *dz_x8;
+  uint32_t *act_pos, *act_zero;   // activity masks [M][ceil(n/32)][Bmax]: bit 31-j of a word = column 32*chunk + j (ActMask)
   uint32_t* res_flags;            // [0]: the batch has a non-zero residual plane (f16f8; written by the batch split)
   float *dw_enc, *dw_dec;         // [M, n, d]
   float *part_enc, *part_dec, *db_part, *bnorm, *l1_over_b, *loss_stage, *nnz_stage;
@@ -183,6 +184,9 @@ static size_t carve(sce_plan* p, const sce_desc& d, uint8_t* base) {
   auto lob = c.take<float>(M);
   auto ls = c.take<float>(M * 4);
   auto ns = c.take<float>(M);
+  const size_t n_chunks = (n + 31) / 32;
+  auto apos = c.take<uint32_t>(M * n_chunks * B);
+  auto azero = c.take<uint32_t>(M * n_chunks * B);
   auto rf = c.take<uint32_t>(64);   // [0] residual flag, [kAbsmaxWord] input range monitor (separate 128-byte lines)
   if (p) {
     p->x_stage = X;
@@ -214,6 +218,8 @@ static size_t carve(sce_plan* p, const sce_desc& d, uint8_t* base) {
     p->loss_stage = ls;
     p->nnz_stage = ns;
     p->res_flags = rf;
+    p->act_pos = apos;
+    p->act_zero = azero;
     p->tiles_mB_max = (int)tiles_mB;
   }
   return align_up(c.off, 1024);
@@ -559,6 +565,12 @@ static int run_pipeline_t(sce_plan* p, const float* x, int B, float* x_hat, bool
     x_is_a.a[0] = p->res_flags;
     x_is_b.b[0] = p->res_flags;
   }
+  ActMask act;
+  act.pos = p->act_pos;
+  act.zero = p->act_zero;
+  act.n_chunks = (n + 31) / 32;
+  act.batch_max = d.batch_max;
+  if (d.variant == SCE_TOPK) act.zero = nullptr;   // relu semantics: no gradient at exactly 0
   // ---- encode
   prof_mark(p, SCE_PHASE_ENCODE, st);
   int n_enc_parts;
@@ -572,6 +584,7 @@ static int run_pipeline_t(sce_plan* p, const float* x, int B, float* x_hat, bool
     ep.part = p->part_enc;
     ep.tiles_m = tiles_mB;
     ep.flag_zero = 1;
+    ep.act = act;
     ep.tiles_n = n > 128 ? (n + 255) / 256 : 1;
     rc = launch_k<EpiEnc, false, false, AR>(n > 128, p->bk_encode, pair_ok(p->pair_encode, B, n), p, maps->encode, 1, xb, one,
                                             dd, d.fwd_passes, B, n, ep, st, x_is_a);
@@ -598,7 +611,7 @@ static int run_pipeline_t(sce_plan* p, const float* x, int B, float* x_hat, bool
     }
     // one block per (row, model); scores / codes of model m start at m * batch_max * n
     topk_select_kernel<AR><<<dim3(B, M), 256, (size_t)n * (use_cand ? 8 : 4), st>>>(
-        reinterpret_cast<const float*>(p->dz_hi), p->b.sparsity, p->c_hi, p->c_lo, p->c_x8, p->part_enc, B, n, Bm * n,
+        reinterpret_cast<const float*>(p->dz_hi), p->b.sparsity, p->c_hi, p->c_lo, p->c_x8, act, p->part_enc, B, n, Bm * n,
         use_cand);
     ++launches;
     CUDA_TRY(cudaGetLastError());
@@ -648,11 +661,9 @@ static int run_pipeline_t(sce_plan* p, const float* x, int B, float* x_hat, bool
     zp.out_hi = maps->st_dz_hi;
     zp.out_lo = maps->st_dz_lo;
     zp.out_x8 = maps->st_dz_x8;
-    zp.c_hi = p->c_hi;
+    zp.act = act;
     zp.l1_over_b = p->l1_over_b;
     zp.db_part = p->b.encoder_bias ? p->db_part : nullptr;
-    zp.c_model_stride = Bm * n;
-    zp.ldc = n;
     zp.tiles_m = tiles_mB;
     rc = launch_k<EpiDco, false, false, AR>(n > 128, p->bk_dcode, pair_ok(p->pair_dcode, B, n), p, maps->dcode, 1, one, one, dd,
                                             p->dcode_passes, B, n, zp, st);

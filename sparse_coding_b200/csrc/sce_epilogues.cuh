@@ -110,12 +110,28 @@ __device__ __forceinline__ void split_pair(float a, float b, int i, uint32_t (&w
 }
 
 // ------------------------------------------------------------------------------------------------
-// encode:  c = relu(acc + bias) -> (c_hi, c_lo);  per-tile partial sums of |c| and count(c > 0)
-// A score of exactly 0 is recorded as c_hi = -0.0 so that the backward pass can reproduce
-// clamp(min=0)'s gradient of 1 at z == 0 without keeping z.
+// Activity masks: what the backward pass needs to know about the forward pass per coefficient is two bits —
+// [c > 0] (the sparsity term and the ReLU gate) and [z == 0] (clamp(min=0) passes the gradient at exactly 0, SURVEY
+// Q4). encode (and the top-k selection) write them as two planes of 32-column words laid out CHUNK-major,
+// word(model, chunk, row) at ((model * n_chunks + chunk) * batch_max + row): the 32 lanes of an epilogue warp own 32
+// consecutive rows, so one coalesced 128-byte request per chunk replaces the 32 scattered 64-byte reads of the code's
+// 16-bit plane the dcode epilogue used to make (1 GB per step at config 2; same-box timing without those reads: -12 %
+// on dcode). Bit (31 - j) of a word is column 32 * chunk + j.
 // ------------------------------------------------------------------------------------------------
-// f16f8: a positive score below the smallest fp16 subnormal would round to +0 and read as "inactive" in the
-// backward pass; it is stored as the smallest subnormal instead (the residual plane carries the difference).
+struct ActMask {
+  uint32_t* pos;    // [M][n_chunks][batch_max]
+  uint32_t* zero;   // same shape: z == 0 exactly; nullptr with relu semantics (top-k), where it would stay empty
+  int n_chunks, batch_max;
+  __device__ __forceinline__ long long at(int model, int chunk, int row) const {
+    return ((long long)model * n_chunks + chunk) * batch_max + row;
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// encode:  c = relu(acc + bias) -> (c_hi, c_lo);  per-tile partial sums of |c| and count(c > 0)
+// [c > 0] and [z == 0] (clamp(min=0)'s gradient of 1 at exactly 0) go to the activity masks, so the
+// backward pass needs neither z nor the code.
+// ------------------------------------------------------------------------------------------------
 template <int ARITH>
 struct EpiEncodeT {
   static constexpr int kCols = 32;
@@ -126,7 +142,8 @@ struct EpiEncodeT {
     const unsigned char* mask;     // [M, n] (1 = coefficient unused) or nullptr
     float* part;                   // [M][tiles_m*8][tiles_n][2]  (sum c, nnz)
     int tiles_m, tiles_n;
-    int flag_zero;                 // 1: mark z == 0 with -0.0 (clamp semantics), 0: relu semantics
+    int flag_zero;                 // 1: record z == 0 (clamp semantics), 0: relu semantics
+    ActMask act;                   // activity masks for the backward pass
   };
   const Params& P;
   const TileCoord& T;
@@ -144,11 +161,13 @@ struct EpiEncodeT {
     uint32_t whi[16], wlo[16];
     const float* bias = P.bias ? P.bias + (long long)T.model * n_total + col : nullptr;
     float ls = 0.f;
-    int cnt = 0;
-    [[maybe_unused]] float zmin = 1.f;
-    [[maybe_unused]] uint32_t neg = 0;
+    uint32_t pos = 0, zero = 0;   // activity-mask words of this row and chunk: bit (31 - j) is column j
     if (col + 32 <= n_total && !P.mask && bias) {
-      // fast path: whole chunk in range, no coefficient mask; bias fetched as 8 uniform float4
+      // fast path: whole chunk in range, no coefficient mask; bias fetched as 8 uniform float4.
+      // Lean on purpose (this GEMM is bound by the SM's data paths, not by the tensor pipe): relu as max, the sign
+      // bits shifted into one word, and ONE tracker — the smallest |z| — for the rare exact zeros, resolved after the loop
+      float zmin = 1.f;
+      uint32_t neg = 0;
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
         const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + j));
@@ -156,44 +175,21 @@ struct EpiEncodeT {
 #pragma unroll
         for (int u = 0; u < 4; u += 2) {
           const float z0 = __uint_as_float(r[j + u]) + bb[u], z1 = __uint_as_float(r[j + u + 1]) + bb[u + 1];
-          if constexpr (ARITH == kArithF16F8) {
-            // lean common case (the epilogue, not the tensor pipe, bounds this GEMM once the main loop is 2 pass
-            // equivalents): relu as max, activity count from the sign bits, and ONE tracker — the smallest |z| —
-            // for the two rare per-element fix-ups (exact zeros, positives below the fp16 range), done after the loop
-            zmin = fminf(zmin, fminf(fabsf(z0), fabsf(z1)));
-            neg = __funnelshift_l(__float_as_uint(z1), __funnelshift_l(__float_as_uint(z0), neg, 1), 1);
-            const float c0 = fmaxf(z0, 0.f), c1 = fmaxf(z1, 0.f);
-            split_pair<ARITH>(c0, c1, (j + u) >> 1, whi, wlo);
-            ls += c0 + c1;
-          } else {
-            const bool p0 = z0 > 0.f, p1 = z1 > 0.f;
-            const float c0 = p0 ? z0 : 0.f, c1 = p1 ? z1 : 0.f;
-            split_pair<ARITH>(c0, c1, (j + u) >> 1, whi, wlo);
-            uint32_t& h2 = whi[(j + u) >> 1];
-            if (P.flag_zero) {
-              if (z0 == 0.f) h2 |= 0x00008000u;
-              if (z1 == 0.f) h2 |= 0x80000000u;
-            }
-            ls += c0 + c1;
-            cnt += int(p0) + int(p1);
-          }
+          zmin = fminf(zmin, fminf(fabsf(z0), fabsf(z1)));
+          neg = __funnelshift_l(__float_as_uint(z1), __funnelshift_l(__float_as_uint(z0), neg, 1), 1);
+          const float c0 = fmaxf(z0, 0.f), c1 = fmaxf(z1, 0.f);
+          split_pair<ARITH>(c0, c1, (j + u) >> 1, whi, wlo);
+          ls += c0 + c1;
         }
       }
-      if constexpr (ARITH == kArithF16F8) {
-        cnt = 32 - __popc(neg);  // no zeros among the 32 scores: positive <=> sign bit clear (fixed below otherwise)
-        if (zmin < 5.9604645e-8f) {  // 2^-24: some |z| is zero or rounds to zero in fp16 — redo the flags per element
-          cnt = 0;
+      pos = ~neg;  // no zero among the 32 scores: positive <=> sign bit clear
+      if (zmin == 0.f) {  // some score is exactly +-0: not positive; recorded for the clamp semantics
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float z = __uint_as_float(r[j]) + __ldg(bias + j);
-            const uint32_t sh = (j & 1) * 16;
-            uint32_t& h2 = whi[j >> 1];
-            if (z > 0.f) {
-              ++cnt;
-              if (((h2 >> sh) & 0xFFFFu) == 0u) h2 |= 1u << sh;
-            } else if (z == 0.f && P.flag_zero) {
-              h2 |= 0x8000u << sh;
-            }
+        for (int j = 0; j < 32; ++j) {
+          const float z = __uint_as_float(r[j]) + __ldg(bias + j);
+          if (z == 0.f) {
+            pos &= ~(0x80000000u >> j);
+            if (P.flag_zero) zero |= 0x80000000u >> j;
           }
         }
       }
@@ -202,30 +198,25 @@ struct EpiEncodeT {
 #pragma unroll
       for (int j = 0; j < 32; j += 2) {
         float cv[2];
-        bool zf[2];
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
           const bool col_ok = col + j + u < n_total;
           const float z = __uint_as_float(r[j + u]) + ((bias && col_ok) ? __ldg(bias + j + u) : 0.f);
           const bool masked = !col_ok || (mask && __ldg(mask + j + u));
           cv[u] = (z > 0.f && !masked) ? z : 0.f;
-          zf[u] = P.flag_zero && z == 0.f && !masked;
+          if (cv[u] > 0.f) pos |= 0x80000000u >> (j + u);
+          if (P.flag_zero && z == 0.f && !masked) zero |= 0x80000000u >> (j + u);
           ls += cv[u];
-          cnt += cv[u] > 0.f ? 1 : 0;
         }
         split_pair<ARITH>(cv[0], cv[1], j >> 1, whi, wlo);
-        uint32_t& h2 = whi[j >> 1];
-        if constexpr (ARITH == kArithF16F8) {
-          if (cv[0] > 0.f && (h2 & 0xFFFFu) == 0u) h2 |= 0x00000001u;
-          if (cv[1] > 0.f && (h2 >> 16) == 0u) h2 |= 0x00010000u;
-        }
-        if (zf[0]) h2 |= 0x00008000u;
-        if (zf[1]) h2 |= 0x80000000u;
       }
     }
     if (row_ok) {
       l1 += ls;
-      nnz += cnt;
+      nnz += __popc(pos);
+      const long long w = P.act.at(T.model, col >> 5, T.row);   // 32 lanes = 32 consecutive rows: coalesced
+      P.act.pos[w] = pos;
+      if (P.act.zero) P.act.zero[w] = zero;
     }
     stage_and_store<ARITH>(stage, T.lane, whi, wlo, &P.out_hi, &P.out_lo, &P.out_x8, col,
                            T.m_blk * kBM + T.warp_q * 32, T.model);
@@ -337,11 +328,9 @@ struct EpiDcodeT {
   static constexpr int kWarpStageBytes = 4096;
   struct Params {
     CUtensorMap out_hi, out_lo, out_x8;  // store maps of the dz planes: [M][B][n], box 32 x 32
-    const __nv_bfloat16* c_hi;     // [M, B, n] 16-bit plane of the code (bf16 or fp16: only sign / zero-ness is read)
+    ActMask act;                   // [c > 0] / [z == 0] written by encode (or the top-k selection)
     const float* l1_over_b;        // [M]: alpha_m / B (f16f8: alpha_m d / 2, see EpiDecodeT)
     float* db_part;                // [M][tiles_m*4][n] or nullptr (no bias)
-    long long c_model_stride;      // batch_max*n
-    int ldc;                       // n
     int tiles_m;
   };
   const Params& P;
@@ -349,59 +338,44 @@ struct EpiDcodeT {
   int m_total, n_total;
   uint8_t* stage;
   float aB;
-  uint4 cn[4];  // the code row's next 32 columns (bf16), fetched one chunk ahead: c_hi streams from HBM
-  __device__ __forceinline__ void fetch_c(int c) {
+  uint32_t pos_n, zero_n;  // the mask words of this warp's next chunk, fetched one chunk ahead
+  __device__ __forceinline__ void fetch_mask(int c) {
     const int col = T.col0 + c;
-    const bool row_ok = T.row < m_total;
-    const __nv_bfloat16* src = P.c_hi + (long long)T.model * P.c_model_stride + (long long)T.row * P.ldc + col;
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-      cn[j] = (row_ok && col + j * 8 < n_total) ? __ldg(reinterpret_cast<const uint4*>(src + j * 8))
-                                                : make_uint4(0, 0, 0, 0);
+    pos_n = zero_n = 0u;
+    if (T.row < m_total && col < n_total) {
+      const long long w = P.act.at(T.model, col >> 5, T.row);
+      pos_n = __ldg(P.act.pos + w);
+      if (P.act.zero) zero_n = __ldg(P.act.zero + w);
+    }
   }
   __device__ EpiDcodeT(const Params& p, const TileCoord& t, int m, int n, uint8_t* st)
       : P(p), T(t), m_total(m), n_total(n), stage(st) {
     aB = __ldg(P.l1_over_b + T.model);
-    fetch_c(T.grp * 32);
+    fetch_mask(T.grp * 32);
   }
 
   __device__ __forceinline__ void chunk(int c, const uint32_t (&r)[32]) {
     const int col = T.col0 + c;
-    uint32_t cw[16];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      cw[4 * j] = cn[j].x;
-      cw[4 * j + 1] = cn[j].y;
-      cw[4 * j + 2] = cn[j].z;
-      cw[4 * j + 3] = cn[j].w;
-    }
-    fetch_c(c + 64);  // this warp's next chunk
+    const uint32_t pos = pos_n, zero = zero_n;
+    fetch_mask(c + 64);  // this warp's next chunk
     if (col >= n_total) return;  // warp-uniform
     float dz[32];
     uint32_t whi[16], wlo[16];
-    // bf16 / fp16 bit patterns of the code: 0x0001..0x7FFF positive (c > 0); 0x8000 is the "z == 0" flag written by
-    // encode (gradient passes, no sparsity term). No flag among this thread's 32 coefficients (the common case):
-    // active <=> the 16-bit pattern is non-zero.
-    uint32_t any = 0;
-#pragma unroll
-    for (int j = 0; j < 16; ++j) any |= cw[j];
-    if ((any & 0x80008000u) == 0u) {
+    if (zero == 0u) {   // the common case: gradient passes exactly where the coefficient is active
 #pragma unroll
       for (int j = 0; j < 32; j += 2) {
-        const float v0 = (cw[j >> 1] & 0x0000FFFFu) ? __uint_as_float(r[j]) + aB : 0.f;
-        const float v1 = (cw[j >> 1] & 0xFFFF0000u) ? __uint_as_float(r[j + 1]) + aB : 0.f;
+        const float v0 = (pos & (0x80000000u >> j)) ? __uint_as_float(r[j]) + aB : 0.f;
+        const float v1 = (pos & (0x40000000u >> j)) ? __uint_as_float(r[j + 1]) + aB : 0.f;
         dz[j] = v0;
         dz[j + 1] = v1;
         split_pair<ARITH>(v0, v1, j >> 1, whi, wlo);
       }
-    } else {
+    } else {            // some z == 0: clamp passes the reconstruction gradient there, without the sparsity term
+      const uint32_t gate = pos | zero;
 #pragma unroll
       for (int j = 0; j < 32; j += 2) {
-        const uint32_t b0 = cw[j >> 1] & 0xFFFFu, b1 = cw[j >> 1] >> 16;
-        const bool pos0 = (b0 - 1u) < 0x7FFFu, pos1 = (b1 - 1u) < 0x7FFFu;
-        const bool gate0 = (b0 - 1u) < 0x8000u, gate1 = (b1 - 1u) < 0x8000u;
-        const float v0 = gate0 ? __uint_as_float(r[j]) + (pos0 ? aB : 0.f) : 0.f;
-        const float v1 = gate1 ? __uint_as_float(r[j + 1]) + (pos1 ? aB : 0.f) : 0.f;
+        const float v0 = (gate & (0x80000000u >> j)) ? __uint_as_float(r[j]) + ((pos & (0x80000000u >> j)) ? aB : 0.f) : 0.f;
+        const float v1 = (gate & (0x40000000u >> j)) ? __uint_as_float(r[j + 1]) + ((pos & (0x40000000u >> j)) ? aB : 0.f) : 0.f;
         dz[j] = v0;
         dz[j + 1] = v1;
         split_pair<ARITH>(v0, v1, j >> 1, whi, wlo);

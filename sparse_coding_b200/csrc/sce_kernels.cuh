@@ -4,7 +4,7 @@
 // Each is a single pass over its data with 16-byte accesses; algorithmic bytes per element are
 // listed in DESIGN.md.
 #pragma once
-#include "sce_gemm.cuh"
+#include "sce_epilogues.cuh"
 
 namespace sce {
 
@@ -436,7 +436,7 @@ template <int ARITH>
 __global__ void __launch_bounds__(256) topk_select_kernel(const float* __restrict__ scores,
                                                           const long long* __restrict__ sparsity,
                                                           void* __restrict__ c_hi, void* __restrict__ c_lo,
-                                                          void* __restrict__ c_x8,
+                                                          void* __restrict__ c_x8, ActMask act,
                                                           float* __restrict__ part /*[M][B][2]*/, int B, int n,
                                                           long long model_stride /*elements between models*/,
                                                           int use_cand /*0: rows too long for a candidate list in smem*/) {
@@ -537,17 +537,33 @@ __global__ void __launch_bounds__(256) topk_select_kernel(const float* __restric
   const uint32_t take_ties = sh_remaining; // number of elements == kth to keep
   const bool all_ties_kept = sh_neq == take_ties;
   float l1 = 0.f, cnt = 0.f;
-  auto emit = [&](int i, float c0, float c1, float c2, float c3) {
-    const float cv4[4] = {c0, c1, c2, c3};
-    store_planes4<ARITH>(cv4, c_hi, c_lo, c_x8, (base >> 2) + i);
-    l1 += c0 + c1 + c2 + c3;
-    cnt += (c0 > 0.f ? 1.f : 0.f) + (c1 > 0.f ? 1.f : 0.f) + (c2 > 0.f ? 1.f : 0.f) + (c3 > 0.f ? 1.f : 0.f);
+  // Called by every thread of the block in lockstep (`valid` false past the end of the row): besides the code planes it
+  // assembles the activity-mask word of each 32-column chunk from the eight threads that own it (relu semantics: the
+  // z == 0 plane stays empty).
+  auto emit = [&](int i, bool valid, float c0, float c1, float c2, float c3) {
+    uint32_t bits = 0;
+    if (valid) {
+      const float cv4[4] = {c0, c1, c2, c3};
+      store_planes4<ARITH>(cv4, c_hi, c_lo, c_x8, (base >> 2) + i);
+      l1 += c0 + c1 + c2 + c3;
+      bits = (c0 > 0.f ? 8u : 0u) | (c1 > 0.f ? 4u : 0u) | (c2 > 0.f ? 2u : 0u) | (c3 > 0.f ? 1u : 0u);
+      cnt += float(__popc(bits));
+    }
+    uint32_t w = bits << (28 - 4 * (i & 7));   // columns 4 (i % 8) .. + 3 of chunk i / 8; bit 31 - j is column j
+    w |= __shfl_xor_sync(0xffffffffu, w, 1);
+    w |= __shfl_xor_sync(0xffffffffu, w, 2);
+    w |= __shfl_xor_sync(0xffffffffu, w, 4);
+    if (valid && (i & 7) == 0) {
+      act.pos[act.at(model, i >> 3, row)] = w;
+    }
   };
   if (all_ties_kept) {
     // the common case (no exact tie straddling the cut): keep = key >= kth; values come back out of the keys
-    for (int i = threadIdx.x; i < n4; i += 256) {
-      const uint4 kk = reinterpret_cast<const uint4*>(keys)[i];
-      emit(i, kk.x >= kth ? key2relu(kk.x) : 0.f, kk.y >= kth ? key2relu(kk.y) : 0.f,
+    for (int i0 = 0; i0 < n4; i0 += 256) {
+      const int i = i0 + threadIdx.x;
+      const bool valid = i < n4;
+      const uint4 kk = valid ? reinterpret_cast<const uint4*>(keys)[i] : make_uint4(0, 0, 0, 0);
+      emit(i, valid, kk.x >= kth ? key2relu(kk.x) : 0.f, kk.y >= kth ? key2relu(kk.y) : 0.f,
            kk.z >= kth ? key2relu(kk.z) : 0.f, kk.w >= kth ? key2relu(kk.w) : 0.f);
     }
   } else {
@@ -571,16 +587,16 @@ __global__ void __launch_bounds__(256) topk_select_kernel(const float* __restric
       __syncthreads();
       uint32_t before = sh_ties_before + (uint32_t)(incl - mine);
       for (int w = 0; w < (threadIdx.x >> 5); ++w) before += warp_cnt[w];
-      if (i < n4) {
+      {
         float cv[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const bool tie = kv[u] == kth;
           const bool keep = kv[u] > kth || (tie && before < take_ties);
           if (tie) ++before;
-          cv[u] = keep ? key2relu(kv[u]) : 0.f;
+          cv[u] = (i < n4 && keep) ? key2relu(kv[u]) : 0.f;
         }
-        emit(i, cv[0], cv[1], cv[2], cv[3]);
+        emit(i, i < n4, cv[0], cv[1], cv[2], cv[3]);
       }
       __syncthreads();
       if (threadIdx.x == 0) {
