@@ -1,9 +1,10 @@
 // sce_engine.cu — libsce.so: the C ABI of include/sce.h on top of the tcgen05 GEMM core and the
 // streaming kernels. One `sce_plan` = one stacked ensemble (FunctionalEnsemble, autoencoders/ensemble.py:68-97).
 //
-// One training step (tied variant; untied and top-k differ as noted) is
-//   split_rows      x -> (x_hi, x_lo)
-//   GEMM encode     z = x W^T (+b) -> relu -> (c_hi, c_lo), sum|c|, nnz          [M x B x n, K = d]
+// One training step (tied variant; untied and top-k differ as noted; "(hi, lo)" stands for the operand planes of the
+// plan's arithmetic: fp16 + two E5M2 planes with f16f8, a bf16 pair with bf16x3) is
+//   split_rows      x -> (x_hi, x_lo)  [+ residual-plane flag, input range monitor]
+//   GEMM encode     z = x W^T (+b) -> relu -> (c_hi, c_lo), activity masks, sum|c|, nnz   [M x B x n, K = d]
 //   GEMM decode     x^ = c W -> r = x^ - x, sum r^2, g = 2r/(Bd) -> (g_hi, g_lo)  [M x B x d, K = n]
 //   GEMM dcode      dz = (g W^T + alpha/B [c>0]) [z>=0] -> (dz_hi, dz_lo), db partials
 //   GEMM dW         dW = dz^T x + c^T g                                            [M x n x d, K = 2B]

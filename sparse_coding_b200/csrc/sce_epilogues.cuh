@@ -1,7 +1,8 @@
 // sce_epilogues.cuh — the fused epilogues of the four GEMMs of one ensemble training step.
 // Each functor is constructed per (thread, tile) by gemm_split_kernel, receives the fp32
 // accumulator of its row in 32-column chunks straight from TMEM, and writes what the next GEMM
-// needs — as (hi, lo) bf16 pairs — so the fp32 code tensor [M,B,n] never exists in HBM.
+// needs — as operand planes (fp16 + two E5M2 planes, or a (hi, lo) bf16 pair; 4 bytes per element either way) — so
+// the fp32 code tensor [M,B,n] never exists in HBM.
 //
 // Reference arithmetic being fused (HoagyC/sparse_coding @ 69c5ae0):
 //   encode  c = clamp(x W^T + b, min=0) [masked_fill]        autoencoders/sae_ensemble.py:141-143, 356

@@ -1,12 +1,15 @@
-// sce_gemm.cuh — persistent, warp-specialised, batched split-bf16 GEMM on tcgen05 / TMEM / TMA.
+// sce_gemm.cuh — persistent, warp-specialised, batched split-operand GEMM on tcgen05 / TMEM / TMA.
 //
 //   D[model][i][j] = sum_set sum_k A_set[model][i,k] * B_set[model][j,k]            (fp32 in TMEM)
 //
-// with every fp32 operand carried as a (hi, lo) bf16 pair, x ~= hi + lo, and the product formed
-// as hi*hi + hi*lo + lo*hi (3 tensor-core passes, relative error ~2^-16; `passes == 1` keeps only
-// hi*hi). This is how the engine reaches the reference's true-FP32 results on the
-// bf16 tensor pipe. Operands may be K-major (reduction index contiguous in HBM) or MN-major
-// (row/column index contiguous), so no transposed copies of activations/codes are ever written.
+// This is how the engine reaches the reference's true-FP32 results on the low-precision tensor
+// pipes. Every fp32 operand is carried as operand planes and the product formed from partial products:
+//   ARITH = bf16x3: x ~= hi + lo (two bf16 planes); hi*hi + hi*lo + lo*hi, three kind::f16 passes (~2^-16);
+//   ARITH = f16f8 : x ~= h + l, h = fp16(x); h*h as one kind::f16 pass, the two cross terms as kind::f8f6f4 passes
+//                   on E5M2 planes at twice the rate, rescaled inside the accumulator (see sce_ptx.cuh) — 2 pass
+//                   equivalents, the default.
+// `passes == 1` keeps only the 16-bit plane product. Operands may be K-major (reduction index contiguous in HBM) or
+// MN-major (row/column index contiguous), so no transposed copies of activations/codes are ever written.
 //
 // One CTA per SM, 384 threads: warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM
 // allocator, warps 4..11 = epilogue (TMEM -> registers -> fused epilogue -> HBM). Accumulators are
