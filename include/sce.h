@@ -99,7 +99,7 @@ enum { SCE_LOSS_TOTAL = 0, SCE_LOSS_RECONSTRUCTION = 1, SCE_LOSS_L1 = 2, SCE_LOS
 int sce_version(void);
 const char* sce_last_error(void);
 
-/* Bytes of device scratch a plan needs (bf16 hi/lo operand copies of the dictionary, the batch, the code, the
+/* Bytes of device scratch a plan needs (operand planes — 4 bytes per element — of the dictionary, the batch, the code, the
  * residual and the code gradient; fp32 weight gradients; reduction partials). */
 size_t sce_workspace_bytes(const sce_desc* desc);
 
@@ -107,7 +107,7 @@ size_t sce_workspace_bytes(const sce_desc* desc);
 int sce_plan_create(const sce_desc* desc, const sce_buffers* buffers, sce_plan** out_plan);
 int sce_plan_destroy(sce_plan* plan);
 
-/* (Re)derive the normalised bf16 hi/lo operand copies of the dictionaries from the fp32 parameters. Must be
+/* (Re)derive the normalised operand planes of the dictionaries from the fp32 parameters. Must be
  * called once before the first step and again whenever the caller modified the parameters itself. */
 int sce_prepare(sce_plan* plan, void* stream);
 

@@ -8,8 +8,8 @@ by Python and are updated in place, so ``unstack``/export/IPC keep working.
 
 What differs is *how* a step is computed. The reference builds ``vmap(grad(sig.loss))`` + ``vmap(torchopt.adam)``
 out of ~70 stock PyTorch launches that stream the fp32 code tensor [M, B, n] through HBM a dozen times. Here
-``step_batch`` is one call into libsce.so (include/sce.h): four tcgen05 split-bf16 GEMMs with fused epilogues plus a
-handful of streaming kernels; the code tensor exists only as a (hi, lo) bf16 pair consumed by the next GEMM.
+``step_batch`` is one call into libsce.so (include/sce.h): four tcgen05 split-operand GEMMs with fused epilogues plus a
+handful of streaming kernels; the code tensor exists only as operand planes (4 bytes per element) consumed by the next GEMM.
 ``aux["c"]`` is therefore a lazy :class:`CodeProxy` — ``aux["c"].count_nonzero(dim=-1).float().mean(dim=-1)``
 (the only use in the reference loop, big_sweep.py:171) is answered from fused counters, and ``.dense()``
 materialises the real [M, B, n] tensor on demand.
@@ -395,7 +395,7 @@ class FunctionalEnsemble:
         return self.grads_batch(minibatches, expand_dims=False)
 
     def refresh(self):
-        """Call after modifying ``params`` / ``buffers`` from outside the engine (re-derives the bf16 operand
+        """Call after modifying ``params`` / ``buffers`` from outside the engine (re-derives the operand
         copies and the cached centring check)."""
         self._centering = None
         if self._plan is not None:
