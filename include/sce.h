@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define SCE_VERSION 101 /* major*10000 + minor*100 + patch */
+#define SCE_VERSION 200 /* major*10000 + minor*100 + patch */
 
 typedef enum sce_status {
   SCE_OK = 0,
@@ -172,6 +172,21 @@ int sce_last_launch_count(const sce_plan* plan);
  * 65504 become inf/NaN in the losses, magnitudes far below 1e-3 lose relative precision: use SCE_ARITH_BF16X3 for
  * such data). BF16X3 plans report 0. */
 int sce_input_absmax(sce_plan* plan, float* out_host, void* stream);
+
+/* Health of the run. *bad_out = 1 when some step since the last sce_prepare / sce_clear_health saw a batch the fp16
+ * operand plane cannot hold (F16F8: |x| >= 65520 or NaN) or produced a non-finite loss. From that step on the Adam
+ * kernels leave parameters, moments and operand planes UNTOUCHED (the update is skipped on the device, so a bad chunk
+ * cannot write NaN into the caller's tensors before the host looks); the caller decides: raise, or rebuild the plan
+ * with SCE_ARITH_BF16X3. *absmax_out as sce_input_absmax. One 512-byte copy and a stream synchronise. */
+int sce_health(sce_plan* plan, int* bad_out, float* absmax_out, void* stream);
+int sce_clear_health(sce_plan* plan, void* stream);
+
+/* Per-feature activation counts of the most recent step / forward: counts[m][j] += number of the B rows whose code
+ * c[m, r, j] is non-zero (device int32 [M, n], ACCUMULATED so that a held-out set can be streamed through in batches).
+ * This is the reference's `(c != 0).sum(0)` (standard_metrics.py:441-454, "features ever active" = count > threshold)
+ * and, divided by the rows, its `(c != 0).float().mean(0)` (:305-308). Reads only the activity-mask plane the encode
+ * epilogue / top-k selection wrote (B/8 bytes per feature chunk): the dense code is never materialised. */
+int sce_active_counts(sce_plan* plan, int B, int* counts, void* stream);
 
 /* The arithmetic the plan resolved to: SCE_ARITH_BF16X3 or SCE_ARITH_F16F8. */
 int sce_plan_arith(const sce_plan* plan);

@@ -24,7 +24,7 @@ EXPORTS = [
     "sce_version", "sce_last_error", "sce_workspace_bytes", "sce_plan_create", "sce_plan_destroy", "sce_prepare",
     "sce_step", "sce_step_host", "sce_forward", "sce_read_code", "sce_grads", "sce_gather_rows",
     "sce_last_launch_count", "sce_get_step_count", "sce_set_step_count", "sce_profile_begin", "sce_profile_end",
-    "sce_plan_arith", "sce_input_absmax",
+    "sce_plan_arith", "sce_input_absmax", "sce_health", "sce_clear_health", "sce_active_counts",
 ]
 PHASES = ["split", "encode", "decode", "losses", "dcode", "dw", "adam"]
 
@@ -88,6 +88,9 @@ def load():
     lib.sce_profile_end.argtypes = [vp, vp, vp]
     lib.sce_plan_arith.argtypes = [vp]
     lib.sce_input_absmax.argtypes = [vp, vp, vp]
+    lib.sce_health.argtypes = [vp, vp, vp, vp]
+    lib.sce_clear_health.argtypes = [vp, vp]
+    lib.sce_active_counts.argtypes = [vp, i, vp, vp]
     for name in EXPORTS:
         getattr(lib, name)  # AttributeError here means header and library disagree
     _lib = lib

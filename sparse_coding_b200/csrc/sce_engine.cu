@@ -52,7 +52,6 @@ struct BatchMaps {
   GemmMaps encode, decode, dcode, dw_enc, dw_dec;
   CUtensorMap st_c_hi, st_c_lo, st_c_x8, st_dz_hi, st_dz_lo, st_dz_x8;  // epilogue TMA-store maps
   cudaGraphExec_t graph;       // captured step for this batch size (launch-bound shapes), or nullptr
-  float *graph_losses, *graph_nnz;
   int graph_launches, eager_steps;
 };
 
@@ -188,7 +187,7 @@ static size_t carve(sce_plan* p, const sce_desc& d, uint8_t* base) {
   const size_t n_chunks = (n + 31) / 32;
   auto apos = c.take<uint32_t>(M * n_chunks * B);
   auto azero = c.take<uint32_t>(M * n_chunks * B);
-  auto rf = c.take<uint32_t>(64);   // [0] residual flag, [kAbsmaxWord] input range monitor (separate 128-byte lines)
+  auto rf = c.take<uint32_t>(kFlagWords);   // [0] residual flag, [kAbsmaxWord] input range monitor, [kBadWord] health (separate 128-byte lines)
   if (p) {
     p->x_stage = X;
     p->x_hi = xh;
@@ -484,14 +483,14 @@ static AdamHyper hyper_for(const sce_plan* p, long long t) {
 template <int MODE, int ARITH>
 static int launch_dict_rows_t(float* e, const float* dw, float* m, float* v, void* hi, void* lo, void* x8,
                               float* grad_out, long long rows, int d, int normalize, float floor, AdamHyper h,
-                              cudaStream_t st) {
+                              const uint32_t* health, cudaStream_t st) {
   const int nv = (d + 511) / 512;
   if (nv == 1)
-    dict_rows_kernel<1, MODE, ARITH><<<(unsigned)rows, 128, 0, st>>>(e, dw, m, v, hi, lo, x8, grad_out, d, normalize, floor, h);
+    dict_rows_kernel<1, MODE, ARITH><<<(unsigned)rows, 128, 0, st>>>(e, dw, m, v, hi, lo, x8, grad_out, d, normalize, floor, h, health);
   else if (nv == 2)
-    dict_rows_kernel<2, MODE, ARITH><<<(unsigned)rows, 128, 0, st>>>(e, dw, m, v, hi, lo, x8, grad_out, d, normalize, floor, h);
+    dict_rows_kernel<2, MODE, ARITH><<<(unsigned)rows, 128, 0, st>>>(e, dw, m, v, hi, lo, x8, grad_out, d, normalize, floor, h, health);
   else
-    dict_rows_kernel<4, MODE, ARITH><<<(unsigned)rows, 128, 0, st>>>(e, dw, m, v, hi, lo, x8, grad_out, d, normalize, floor, h);
+    dict_rows_kernel<4, MODE, ARITH><<<(unsigned)rows, 128, 0, st>>>(e, dw, m, v, hi, lo, x8, grad_out, d, normalize, floor, h, health);
   CUDA_TRY(cudaGetLastError());
   return SCE_OK;
 }
@@ -504,8 +503,8 @@ static int launch_dict_rows(const sce_plan* p, int which, float* e, const float*
   void* x8 = which ? (void*)p->wdec_x8 : (void*)p->wenc_x8;
   if (MODE == MODE_GRAD) hi = lo = x8 = nullptr;
   return p->arith == kArithF16F8
-             ? launch_dict_rows_t<MODE, kArithF16F8>(e, dw, m, v, hi, lo, x8, grad_out, rows, d, normalize, floor, h, st)
-             : launch_dict_rows_t<MODE, kArithBf16x3>(e, dw, m, v, hi, lo, x8, grad_out, rows, d, normalize, floor, h, st);
+             ? launch_dict_rows_t<MODE, kArithF16F8>(e, dw, m, v, hi, lo, x8, grad_out, rows, d, normalize, floor, h, p->res_flags, st)
+             : launch_dict_rows_t<MODE, kArithBf16x3>(e, dw, m, v, hi, lo, x8, grad_out, rows, d, normalize, floor, h, p->res_flags, st);
 }
 
 // f16f8 runs the backward pass on the residual r instead of g = 2r/(B d) (EpiDecodeT): weight- and bias-gradient
@@ -651,7 +650,8 @@ static int run_pipeline_t(sce_plan* p, const float* x, int B, float* x_hat, bool
     ++launches;
   }
   finalize_kernel<<<M, 256, 0, st>>>(p->part_enc, n_enc_parts, p->part_dec, tiles_mB * 8 * dp.tiles_n, p->b.l1_alpha,
-                                     p->b.encoder_bias ? p->b.bias_decay : nullptr, p->bnorm, B, dd, out_losses, out_nnz);
+                                     p->b.encoder_bias ? p->b.bias_decay : nullptr, p->bnorm, B, dd, out_losses, out_nnz,
+                                     p->res_flags);
   ++launches;
   CUDA_TRY(cudaGetLastError());
 
@@ -817,7 +817,7 @@ int sce_plan_destroy(sce_plan* plan) {
 int sce_prepare(sce_plan* p, void* stream) {
   if (!p) return fail(SCE_ERR_INVALID, "plan is NULL");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  CUDA_TRY(cudaMemsetAsync(p->res_flags, 0, 64 * sizeof(uint32_t), st));   // residual flag + input range monitor
+  CUDA_TRY(cudaMemsetAsync(p->res_flags, 0, kFlagWords * sizeof(uint32_t), st));   // residual flag, input range monitor, health
   const sce_desc& d = p->d;
   const long long rows = (long long)d.n_models * d.n;
   AdamHyper h = hyper_for(p, 1);
@@ -865,7 +865,7 @@ static int step_launches(sce_plan* p, const float* x, int B, float* out_losses, 
     const int n_part = ((B + kBM - 1) / kBM) * 4;
     bias_kernel<MODE_ADAM><<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(
         p->b.encoder_bias, p->b.bias_m, p->b.bias_v, p->db_part, n_part, d.n, d.n_models, p->b.bias_decay, p->bnorm,
-        nullptr, h, grad_out_scale(p, B));
+        nullptr, h, grad_out_scale(p, B), p->res_flags);
     CUDA_TRY(cudaGetLastError());
     ++launches;
   }
@@ -877,7 +877,8 @@ static int step_launches(sce_plan* p, const float* x, int B, float* out_losses, 
 // Launch-bound shapes (a step of ~10 kernels that each run a few microseconds, e.g. BASELINE config 1) replay the
 // step as one CUDA graph: the batch is first copied into the plan's staging buffer so that every kernel argument is
 // stable, the graph is captured on the second step at a given batch size (the first one runs eagerly and performs
-// the one-off cudaFuncSetAttribute calls) and re-captured if the caller's output pointers change.
+// the one-off cudaFuncSetAttribute calls); the captured kernels write the plan's staging outputs, which are copied to
+// the caller's buffers after the launch.
 static bool graph_eligible(const sce_plan* p) {
   if (p->prof_on) return false;                                   // per-phase events are recorded eagerly
   if (p->d.adam_count_mode != SCE_ADAM_FROZEN_T1) return false;   // bias correction is a kernel argument that moves
@@ -898,25 +899,24 @@ int sce_step(sce_plan* p, const float* x, int B, float* out_losses, float* out_n
     if (rc) return rc;
     const size_t bytes = (size_t)p->xm * B * p->d.d * sizeof(float);
     if (x != p->x_stage) CUDA_TRY(cudaMemcpyAsync(p->x_stage, x, bytes, cudaMemcpyDeviceToDevice, st));
-    if (maps->graph && (maps->graph_losses != out_losses || maps->graph_nnz != out_nnz)) {
-      cudaGraphExecDestroy(maps->graph);
-      maps->graph = nullptr;
-      maps->eager_steps = 1;
-    }
+    // the captured kernels write the plan's own staging outputs (stable addresses: callers may pass fresh tensors
+    // every step, as the reference returns them); the results are copied out below
+    float* const cap_losses = p->loss_stage;
+    float* const cap_nnz = p->nnz_stage;
     if (maps->graph) {
       CUDA_TRY(cudaGraphLaunch(maps->graph, st));
       p->last_launches = maps->graph_launches;
       rc = SCE_OK;
     } else if (maps->eager_steps == 0) {
       maps->eager_steps = 1;
-      rc = step_launches(p, p->x_stage, B, out_losses, out_nnz, 1, st);
+      rc = step_launches(p, p->x_stage, B, cap_losses, cap_nnz, 1, st);
     } else {
       // capture on a private stream (the caller's may be the legacy default stream, which cannot be captured);
       // capturing records the launches without running them, the instantiated graph is launched on `st`
       cudaGraph_t g = nullptr;
       if (!p->cap_stream) CUDA_TRY(cudaStreamCreateWithFlags(&p->cap_stream, cudaStreamNonBlocking));
       CUDA_TRY(cudaStreamBeginCapture(p->cap_stream, cudaStreamCaptureModeThreadLocal));
-      rc = step_launches(p, p->x_stage, B, out_losses, out_nnz, 1, p->cap_stream);
+      rc = step_launches(p, p->x_stage, B, cap_losses, cap_nnz, 1, p->cap_stream);
       cudaError_t ce = cudaStreamEndCapture(p->cap_stream, &g);
       if (rc == SCE_OK && ce == cudaSuccess && g) {
         cudaGraphExec_t ge = nullptr;
@@ -924,8 +924,6 @@ int sce_step(sce_plan* p, const float* x, int B, float* out_losses, float* out_n
         cudaGraphDestroy(g);
         if (ce != cudaSuccess) return fail(SCE_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ce));
         maps->graph = ge;
-        maps->graph_losses = out_losses;
-        maps->graph_nnz = out_nnz;
         maps->graph_launches = p->last_launches;
         CUDA_TRY(cudaGraphLaunch(maps->graph, st));
       } else {
@@ -934,6 +932,11 @@ int sce_step(sce_plan* p, const float* x, int B, float* out_losses, float* out_n
         if (rc == SCE_OK) return fail(SCE_ERR_CUDA, "stream capture of the step failed: %s", cudaGetErrorString(ce));
       }
     }
+    if (rc == SCE_OK && out_losses && out_losses != cap_losses)
+      CUDA_TRY(cudaMemcpyAsync(out_losses, cap_losses, (size_t)p->d.n_models * SCE_LOSS_COLS * sizeof(float),
+                               cudaMemcpyDeviceToDevice, st));
+    if (rc == SCE_OK && out_nnz && out_nnz != cap_nnz)
+      CUDA_TRY(cudaMemcpyAsync(out_nnz, cap_nnz, (size_t)p->d.n_models * sizeof(float), cudaMemcpyDeviceToDevice, st));
   }
   if (rc) return rc;
   p->step += 1;
@@ -970,7 +973,7 @@ int sce_grads(sce_plan* p, const float* x, int B, float* d_encoder, float* d_bia
     const int n_part = ((B + kBM - 1) / kBM) * 4;
     bias_kernel<MODE_GRAD><<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(
         p->b.encoder_bias, nullptr, nullptr, p->db_part, n_part, d.n, d.n_models, p->b.bias_decay, p->bnorm, d_bias, h,
-        grad_out_scale(p, B));
+        grad_out_scale(p, B), nullptr);
     CUDA_TRY(cudaGetLastError());
   }
   return SCE_OK;
@@ -1036,6 +1039,35 @@ int sce_input_absmax(sce_plan* plan, float* out_host, void* stream) {
   memcpy(out_host, &bits, sizeof(bits));
   return SCE_OK;
 }
+int sce_health(sce_plan* plan, int* bad_out, float* absmax_out, void* stream) {
+  if (!plan) return fail(SCE_ERR_INVALID, "plan is NULL");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint32_t words[kFlagWords];
+  CUDA_TRY(cudaMemcpyAsync(words, plan->res_flags, sizeof(words), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  if (bad_out) *bad_out = words[kBadWord] != 0u;
+  if (absmax_out) {
+    *absmax_out = 0.f;
+    if (plan->arith == kArithF16F8) memcpy(absmax_out, &words[kAbsmaxWord], sizeof(float));
+  }
+  return SCE_OK;
+}
+int sce_clear_health(sce_plan* plan, void* stream) {
+  if (!plan) return fail(SCE_ERR_INVALID, "plan is NULL");
+  CUDA_TRY(cudaMemsetAsync(plan->res_flags + kBadWord, 0, sizeof(uint32_t), static_cast<cudaStream_t>(stream)));
+  return SCE_OK;
+}
+
+int sce_active_counts(sce_plan* plan, int B, int* counts, void* stream) {
+  if (!plan || !counts) return fail(SCE_ERR_INVALID, "plan / counts is NULL");
+  if (B < 1 || B > plan->d.batch_max) return fail(SCE_ERR_INVALID, "B = %d outside [1, batch_max = %d]", B, plan->d.batch_max);
+  const int n_chunks = (plan->d.n + 31) / 32;
+  active_count_kernel<<<dim3(n_chunks, plan->d.n_models), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      plan->act_pos, n_chunks, plan->d.batch_max, B, plan->d.n, counts);
+  CUDA_TRY(cudaGetLastError());
+  return SCE_OK;
+}
+
 int sce_plan_arith(const sce_plan* plan) {
   return !plan ? 0 : plan->arith == kArithF16F8 ? SCE_ARITH_F16F8 : SCE_ARITH_BF16X3;
 }

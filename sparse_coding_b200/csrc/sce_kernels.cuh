@@ -38,6 +38,15 @@ __device__ __forceinline__ void store_planes4(const float (&v)[4], void* hi, voi
 // flag word, every warp's store to the flag would bounce the line the monitor's read needs (measured: 0.29 ms
 // instead of 0.03 ms for the 16 MB batch split on inexact data).
 constexpr int kAbsmaxWord = 32;
+// res_flag[kBadWord] != 0: "this step must not update the parameters" — the batch split saw a value the fp16 operand
+// plane cannot hold (|x| >= 65520 or NaN), or the loss finalisation saw a non-finite loss. The Adam kernels read it
+// and leave parameters, moments and operand planes untouched, so an out-of-range chunk cannot poison the run before
+// the host looks (sce_health); sticky until sce_prepare / sce_clear_health. Own 128-byte line, like the monitor.
+constexpr int kBadWord = 64;
+constexpr int kFlagWords = 128;
+__device__ __forceinline__ bool step_is_bad(const uint32_t* __restrict__ flags) {
+  return flags != nullptr && *reinterpret_cast<const volatile uint32_t*>(flags + kBadWord) != 0u;
+}
 template <int ARITH>
 __global__ void split_rows_kernel(const float* __restrict__ x, void* __restrict__ hi, void* __restrict__ lo,
                                   void* __restrict__ x8, long long n4, uint32_t* __restrict__ res_flag) {
@@ -68,6 +77,8 @@ __global__ void split_rows_kernel(const float* __restrict__ x, void* __restrict_
       // non-negative floats order like their bit patterns (a NaN input has the largest pattern and sticks)
       if ((threadIdx.x & 31) == 0 && __float_as_uint(amax) > res_flag[kAbsmaxWord])
         atomicMax(res_flag + kAbsmaxWord, __float_as_uint(amax));
+      // 65520 is the smallest magnitude that rounds to inf in fp16; a NaN has a larger bit pattern still
+      if ((threadIdx.x & 31) == 0 && __float_as_uint(amax) >= 0x477FF000u) res_flag[kBadWord] = 1u;
     }
   }
 }
@@ -165,8 +176,10 @@ __global__ void __launch_bounds__(128) dict_rows_kernel(float* __restrict__ e, c
                                                         float* __restrict__ m, float* __restrict__ v,
                                                         void* __restrict__ w_hi, void* __restrict__ w_lo,
                                                         void* __restrict__ w_x8, float* __restrict__ grad_out, int d,
-                                                        int normalize, float floor, AdamHyper h) {
+                                                        int normalize, float floor, AdamHyper h,
+                                                        const uint32_t* __restrict__ health) {
   __shared__ float red[8];
+  if (MODE == MODE_ADAM && step_is_bad(health)) return;   // block-uniform: see kBadWord
   const long long row = blockIdx.x;
   const long long base = row * d;
   float4 ev[NV], gv[NV];
@@ -272,9 +285,11 @@ template <int MODE>
 __global__ void bias_kernel(float* __restrict__ bias, float* __restrict__ m, float* __restrict__ v,
                             const float* __restrict__ db_part, int n_part, int n, int n_models,
                             const float* __restrict__ bias_decay, const float* __restrict__ bnorm,
-                            float* __restrict__ grad_out, AdamHyper h, float part_scale) {
+                            float* __restrict__ grad_out, AdamHyper h, float part_scale,
+                            const uint32_t* __restrict__ health) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)n_models * n) return;
+  if (MODE == MODE_ADAM && step_is_bad(health)) return;
   const int model = int(i / n);
   const int j = int(i - (long long)model * n);
   const float* p = db_part + (long long)model * n_part * n + j;
@@ -305,7 +320,8 @@ __global__ void __launch_bounds__(256) finalize_kernel(const float* __restrict__
                                                        const float* __restrict__ l1_alpha,
                                                        const float* __restrict__ bias_decay,
                                                        const float* __restrict__ bnorm, int B, int d,
-                                                       float* __restrict__ out, float* __restrict__ nnz) {
+                                                       float* __restrict__ out, float* __restrict__ nnz,
+                                                       uint32_t* __restrict__ health) {
   __shared__ double red[3][8];
   const int model = blockIdx.x;
   double l1 = 0, cnt = 0, sq = 0;
@@ -340,6 +356,7 @@ __global__ void __launch_bounds__(256) finalize_kernel(const float* __restrict__
     const float l_rec = (float)(c / ((double)B * d));
     const float l_l1 = l1_alpha ? (float)(l1_alpha[model] * (a / B)) : 0.f;
     const float l_bd = (bias_decay && bnorm) ? bias_decay[model] * bnorm[model] : 0.f;
+    if (health && !isfinite(l_rec + l_l1 + l_bd)) health[kBadWord] = 1u;   // the Adam kernels of this step skip
     if (out) {
       out[model * 4 + 0] = l_rec + l_l1 + l_bd;
       out[model * 4 + 1] = l_rec;
@@ -347,6 +364,41 @@ __global__ void __launch_bounds__(256) finalize_kernel(const float* __restrict__
       out[model * 4 + 3] = l_bd;
     }
     if (nnz) nnz[model] = (float)(b / B);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-feature activation counts (standard_metrics.py:305-308 `(c != 0).float().mean(0)` and :441-454
+// `n_active_count += (c != 0).sum(0)`; "ever active" = count > threshold): column sums of the [c > 0] activity-mask
+// plane over the batch rows. One block per (32-column chunk, model): every lane holds the mask word of one row, a
+// ballot per bit position counts 32 rows at once. counts[model][32 chunk + j] += sum_r bit(31 - j) of
+// pos[model][chunk][r], accumulated across calls so a held-out set can be streamed through in batches. Reads B words
+// per block, coalesced (the plane is chunk-major); the dense code is never touched.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) active_count_kernel(const uint32_t* __restrict__ pos, int n_chunks, int batch_max,
+                                                           int B, int n, int* __restrict__ counts) {
+  __shared__ int red[8][32];
+  const int chunk = blockIdx.x, model = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t* p = pos + ((long long)model * n_chunks + chunk) * batch_max;
+  int mine = 0;   // lane j accumulates the count of column j of the chunk
+  for (int r0 = warp * 32; r0 < B; r0 += 256) {
+    const int r = r0 + lane;
+    const uint32_t w = r < B ? __ldg(p + r) : 0u;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int c = __popc(__ballot_sync(0xffffffffu, (w >> (31 - j)) & 1u));
+      if (lane == j) mine += c;
+    }
+  }
+  red[warp][lane] = mine;
+  __syncthreads();
+  if (warp == 0) {
+    int t = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i][lane];
+    const int col = chunk * 32 + lane;
+    if (col < n) counts[(long long)model * n + col] += t;
   }
 }
 

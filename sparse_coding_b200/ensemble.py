@@ -15,10 +15,19 @@ handful of streaming kernels; the code tensor exists only as operand planes (4 b
 materialises the real [M, B, n] tensor on demand.
 
 There is no CPU path and no generic-autograd path: a signature without an engine ``variant`` raises.
+
+Range contract of the default arithmetic (``arith="auto"`` -> f16f8 where the shape allows, include/sce.h): operand
+values must fit fp16. The engine guards this on the device — a batch holding |x| >= 65520 / NaN, or a step whose loss
+is not finite, SKIPS its Adam update (parameters, moments and operand planes stay untouched) and raises a sticky
+health flag. ``step_batch`` reads that flag after the first step of a plan and every ``health_check_every`` steps
+(one small D2H copy), ``check_health()`` on demand (the chunk loops call it at the end of every chunk): with
+``arith="auto"`` the ensemble then rebuilds its plan on the fp32-range bf16x3 arithmetic, re-runs the current batch
+and warns; with an explicitly requested arithmetic it raises ``FloatingPointError``.
 """
 from __future__ import annotations
 
 import ctypes as C
+import warnings
 from typing import Dict, List, Optional
 
 import torch
@@ -142,14 +151,15 @@ class CodeProxy:
 class FunctionalEnsemble:
     def __init__(self, models, sig, optimizer_func, optimizer_kwargs, device=None, no_stacking=False,
                  adam_count_mode: str = "frozen_t1", fwd_passes: int = 3, bwd_passes: int = 3,
-                 materialize_code: bool = False, arith: str = "auto"):
+                 materialize_code: bool = False, arith: str = "auto", health_check_every: int = 64):
         """``models``: list of (params, buffers) from ``sig.init``; ``optimizer_func``: ``torchopt.adam`` (if
         installed), :func:`sparse_coding_b200.optim.adam`, or the string "adam"; ``optimizer_kwargs``: ``{"lr": …}``.
         ``no_stacking`` is accepted for API compatibility (the reference needs it for TopK because ``torch.topk``
         with a data-dependent k cannot be vmapped; the engine batches TopK models natively).
         Extra keywords (engine-only): ``adam_count_mode`` "frozen_t1" (reference behaviour) or
         "standard"; ``fwd_passes`` / ``bwd_passes`` 3 (split operands, fp32-grade) or 1 (16-bit plane only);
-        ``arith`` "auto" | "bf16x3" | "f16f8": how fp32 operands reach the tensor cores (include/sce.h, sce_arith)."""
+        ``arith`` "auto" | "bf16x3" | "f16f8": how fp32 operands reach the tensor cores (include/sce.h, sce_arith);
+        ``health_check_every``: steps between reads of the device-side health flag (module docstring; 0 = never)."""
         if device is None:
             first = next(iter(models[0][0].values()))
             self.device = first.device
@@ -170,6 +180,7 @@ class FunctionalEnsemble:
             raise ValueError(f"arith must be one of {sorted(_lib.ARITH_CODE)}, got {arith!r}")
         self.arith = arith
         self.materialize_code = materialize_code
+        self.health_check_every = int(health_check_every)
         self.optim_states = {
             "mu": _tree_map(torch.zeros_like, self.params),
             "nu": _tree_map(torch.zeros_like, self.params),
@@ -196,6 +207,9 @@ class FunctionalEnsemble:
         self._main = main
         self._n, self._d = self.params[main].shape[1], self.params[main].shape[2]
         self._engine_buffers = None
+        self._arith_fallback = None       # "bf16x3" once an auto plan left the fp16 range (sticky for this object)
+        self._since_health = 0            # steps since the health flag was last read
+        self._plan_steps = 0              # steps taken on the current plan
 
     # ------------------------------------------------------------------------------------------------------
     # engine plumbing
@@ -240,7 +254,7 @@ class FunctionalEnsemble:
             adam_count_mode=_lib.SCE_ADAM_FROZEN_T1 if self.adam_count_mode == "frozen_t1" else _lib.SCE_ADAM_STANDARD,
             fwd_passes=self.fwd_passes, bwd_passes=self.bwd_passes,
             norm_floor=0.0 if self._variant == "topk" else 1e-8,
-            arith=_lib.ARITH_CODE[getattr(self, "arith", "auto")])
+            arith=_lib.ARITH_CODE[getattr(self, "_arith_fallback", None) or getattr(self, "arith", "auto")])
         nbytes = lib.sce_workspace_bytes(C.byref(desc))
         if nbytes == 0:
             _lib.check(-1, "sce_workspace_bytes")
@@ -286,8 +300,16 @@ class FunctionalEnsemble:
             self._plan_key = (batch_max, bool(x_per_model))
             _lib.check(lib.sce_set_step_count(plan, self._steps), "sce_set_step_count")
             _lib.check(lib.sce_prepare(plan, self._stream()), "sce_prepare")
-        self._out_losses = torch.empty(M, _lib.SCE_LOSS_COLS, dtype=torch.float32, device=dev)
-        self._out_nnz = torch.empty(M, dtype=torch.float32, device=dev)
+        self._plan_steps = 0
+        self._since_health = 0
+        self._new_outputs()
+
+    def _new_outputs(self):
+        """Fresh result tensors for the next engine call (the reference returns new tensors every step; allocating
+        them from torch's caching allocator costs no kernel, unlike cloning a fixed output buffer)."""
+        dev = torch.device(self.device)
+        self._out_losses = torch.empty(self.n_models, _lib.SCE_LOSS_COLS, dtype=torch.float32, device=dev)
+        self._out_nnz = torch.empty(self.n_models, dtype=torch.float32, device=dev)
 
     def _destroy_plan(self):
         if getattr(self, "_plan", None) is not None:
@@ -326,16 +348,23 @@ class FunctionalEnsemble:
         return x, B
 
     def _losses_dict(self) -> Dict[str, Tensor]:
-        cols = self._out_losses.clone()
+        cols = self._out_losses
         return {k: cols[:, i] for i, k in enumerate(("loss", "l_reconstruction", "l_l1", "l_bias_decay"))
                 if k in _LOSS_KEYS[self._variant]}
 
     def _aux(self, B):
         self._serial += 1
-        proxy = CodeProxy(self, B, self._out_nnz.clone(), self._serial)
+        proxy = CodeProxy(self, B, self._out_nnz, self._serial)
         if self.materialize_code:
             return {"c": proxy.dense()}
         return {"c": proxy}
+
+    def _results(self, B):
+        """(loss_data, aux) of the engine call that just wrote the current output tensors; hands those tensors to
+        the caller and allocates fresh ones for the next call."""
+        out = (self._losses_dict(), self._aux(B))
+        self._new_outputs()
+        return out
 
     def _read_code(self, B) -> Tensor:
         out = torch.empty(self.n_models, B, self._n, dtype=torch.float32, device=self.device)
@@ -349,15 +378,69 @@ class FunctionalEnsemble:
     def step_batch(self, minibatches, expand_dims=True):
         """One Adam step of every model on one batch (ensemble.py:175-193). Returns (loss_data, aux)."""
         with torch.no_grad():
-            x, B = self._prep_batch(minibatches, expand_dims)
-            with torch.cuda.device(x.device):
-                _lib.check(_lib.load().sce_step(self._plan, x.data_ptr(), B, self._out_losses.data_ptr(),
-                                                self._out_nnz.data_ptr(), self._stream()), "sce_step")
+            every = getattr(self, "health_check_every", 64)
+            while True:
+                x, B = self._prep_batch(minibatches, expand_dims)
+                self._launch_step(x, B)
+                self._plan_steps += 1
+                self._since_health += 1
+                if not every or not (self._plan_steps == 1 or self._since_health >= every):
+                    break
+                if self._health_action(rerun=True) != "rerun":
+                    break
+                # the plan was rebuilt on bf16x3 (the update of this batch was skipped on the device): take the step again
             self._steps += 1
             if self.adam_count_mode != "frozen_t1":
                 for t in self.optim_states["count"].values():
                     t.add_(1)
-            return self._losses_dict(), self._aux(B)
+            return self._results(B)
+
+    def _launch_step(self, x, B):
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.load().sce_step(self._plan, x.data_ptr(), B, self._out_losses.data_ptr(),
+                                            self._out_nnz.data_ptr(), self._stream()), "sce_step")
+
+    # ------------------------------------------------------------------------------------------------------
+    # health (range contract of the f16f8 arithmetic, non-finite losses)
+    # ------------------------------------------------------------------------------------------------------
+    def health(self):
+        """(bad, absmax) from the device: ``bad`` — some step since the plan was prepared skipped its update because
+        the batch left the fp16 range or the loss was not finite; ``absmax`` — largest |x| fed (f16f8 plans)."""
+        if self._plan is None:
+            return False, 0.0
+        bad, amax = C.c_int(0), C.c_float(0.0)
+        with torch.cuda.device(torch.device(self.device)):
+            _lib.check(_lib.load().sce_health(self._plan, C.byref(bad), C.byref(amax), self._stream()), "sce_health")
+        self._since_health = 0
+        return bool(bad.value), float(amax.value)
+
+    def _health_action(self, rerun=None):
+        bad, amax = self.health()
+        if not bad:
+            return "ok"
+        resolved = self.resolved_arith()
+        lost = max(self._plan_steps - 1, 0) if rerun else self._plan_steps
+        lost = min(lost, getattr(self, "health_check_every", 64))
+        if resolved == "f16f8" and getattr(self, "arith", "auto") == "auto":
+            self._arith_fallback = "bf16x3"
+            key = self._plan_key
+            self._build_plan(key[0], key[1])
+            warnings.warn(
+                f"a batch left the range of the f16f8 operand arithmetic (largest |activation| {amax:g}; fp16 holds "
+                "|v| < 65504) or produced a non-finite loss: the affected updates were skipped on the device, the "
+                f"ensemble now runs on arith='bf16x3' (fp32 range). Up to {lost} earlier step(s) since the last health "
+                "check made no update.", RuntimeWarning)
+            return "rerun"
+        raise FloatingPointError(
+            f"the engine skipped parameter updates: largest |activation| fed = {amax:g}, arithmetic = {resolved} "
+            + ("(values beyond 65504 do not fit its fp16 operand plane: construct the ensemble with arith='bf16x3' "
+               "or arith='auto')" if resolved == "f16f8" else "(a loss was not finite)")
+            + "; parameters and Adam moments were left untouched by the offending steps")
+
+    def check_health(self) -> None:
+        """Read the device-side health flag now (the chunk loops call this at the end of every chunk)."""
+        if self._plan is not None:
+            self._health_action(rerun=None)
 
     def forward_batch(self, minibatches, expand_dims=True, return_x_hat=False):
         """Forward only: losses and code statistics (and optionally x̂ [M,B,d]) without touching parameters."""
@@ -369,7 +452,7 @@ class FunctionalEnsemble:
                                                    x_hat.data_ptr() if return_x_hat else None,
                                                    self._out_losses.data_ptr(), self._out_nnz.data_ptr(),
                                                    self._stream()), "sce_forward")
-            out = (self._losses_dict(), self._aux(B))
+            out = self._results(B)
             return out + (x_hat,) if return_x_hat else out
 
     def grads_batch(self, minibatches, expand_dims=True):
@@ -382,7 +465,7 @@ class FunctionalEnsemble:
                 _lib.check(_lib.load().sce_grads(self._plan, x.data_ptr(), B, ptr(self._main), ptr("encoder_bias"),
                                                  ptr("decoder"), self._out_losses.data_ptr(),
                                                  self._out_nnz.data_ptr(), self._stream()), "sce_grads")
-            return g, (self._losses_dict(), self._aux(B))
+            return g, self._results(B)
 
     def calc_grads(self, params, buffers, minibatches):
         """Reference-shaped entry point (``self.calc_grads`` of ensemble.py:99-123): gradients of ``sig.loss`` for
@@ -399,8 +482,13 @@ class FunctionalEnsemble:
         copies and the cached centring check)."""
         self._centering = None
         if self._plan is not None:
+            # engine-side copies of the buffers (dtype-converted hyper-parameter vectors, uint8 coef_mask, int64
+            # sparsity) keep their addresses — the plan holds the pointers — and are refilled in place
+            for name, t in (self._engine_buffers or {}).items():
+                t.copy_(self.buffers[name].to(device=t.device, dtype=t.dtype))
             with torch.cuda.device(torch.device(self.device)):
                 _lib.check(_lib.load().sce_prepare(self._plan, self._stream()), "sce_prepare")
+            self._plan_steps = 0
 
     def profile_begin(self):
         """Start per-phase device timing of the following ``step_batch`` calls (up to 64 steps)."""
@@ -439,6 +527,23 @@ class FunctionalEnsemble:
             _lib.check(_lib.load().sce_input_absmax(self._plan, C.byref(out), self._stream()), "sce_input_absmax")
         return float(out.value)
 
+    def active_counts(self, B: int, counts: Optional[Tensor] = None) -> Tensor:
+        """Add, per model and feature, the number of the ``B`` rows of the most recent engine call whose code is
+        non-zero to ``counts`` ([M, n] int32 on the device; created zeroed when None) and return it — the reference's
+        ``(c != 0).sum(0)`` (standard_metrics.py:441-454; ``/ rows`` gives :305-308). Fused: column sums of the
+        activity-mask plane the encode epilogue wrote; the dense code is never materialised."""
+        if self._plan is None:
+            raise RuntimeError("active_counts needs a built plan: run forward_batch / step_batch first")
+        dev = torch.device(self.device)
+        if counts is None:
+            counts = torch.zeros(self.n_models, self._n, dtype=torch.int32, device=dev)
+        if counts.dtype != torch.int32 or tuple(counts.shape) != (self.n_models, self._n) or not counts.is_contiguous():
+            raise ValueError("counts must be a contiguous int32 tensor of shape [n_models, n]")
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().sce_active_counts(self._plan, int(B), counts.data_ptr(), self._stream()),
+                       "sce_active_counts")
+        return counts
+
     def unstack(self, device=None):
         params = unstack_dict(self.params, self.n_models, device=device)
         buffers = unstack_dict(self.buffers, self.n_models, device=device)
@@ -451,7 +556,8 @@ class FunctionalEnsemble:
             "sig": self.sig, "no_stacking": self.no_stacking, "optimizer_func": self.optimizer_func,
             "optimizer_kwargs": self.optimizer_kwargs, "optim_states": self.optim_states,
             "adam_count_mode": self.adam_count_mode, "fwd_passes": self.fwd_passes, "bwd_passes": self.bwd_passes,
-            "arith": getattr(self, "arith", "auto"),
+            "arith": getattr(self, "arith", "auto"), "arith_fallback": getattr(self, "_arith_fallback", None),
+            "health_check_every": getattr(self, "health_check_every", 64),
             "materialize_code": self.materialize_code, "steps": self._steps,
         }
 
@@ -466,9 +572,18 @@ class FunctionalEnsemble:
         self.fwd_passes = state_dict.get("fwd_passes", 3)
         self.bwd_passes = state_dict.get("bwd_passes", 3)
         self.materialize_code = state_dict.get("materialize_code", False)
+        self.health_check_every = state_dict.get("health_check_every", 64)
         self.optimizer = resolve_optimizer(self.optimizer_func, self.optimizer_kwargs)
         self.init_functions()
+        self._arith_fallback = state_dict.get("arith_fallback")
         self._steps = state_dict.get("steps", 0)
+        if self.adam_count_mode != "frozen_t1":
+            # The reference's dispatch hands state_dict() to a freshly spawned worker per chunk (cluster_runs.py:113-125):
+            # the worker's Python step counter dies with it, but optim_states["count"] is shared memory updated in
+            # place, so the bias correction continues from there.
+            counts = [int(t.max()) for t in self.optim_states.get("count", {}).values() if t.numel()]
+            if counts:
+                self._steps = max(self._steps, max(counts))
         return self
 
     def to_device(self, device):

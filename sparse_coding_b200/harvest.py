@@ -126,9 +126,11 @@ def make_activation_dataset_hf(sentence_dataset, model: torch.nn.Module, tensor_
             sink.copied[slot] = ev
             host = sink.pinned[slot][:rows]
 
-            def job(ev=ev, host=host):
+            def job(ev=ev, host=host, full=rows == sink.rows):
                 ev.synchronize()
-                return save_activation_chunk(host, chunk_idx, sink.folder)
+                # torch.save serialises the whole underlying storage of a view: an undersized final chunk is written
+                # from a compact copy (the reference writes a compact torch.cat result, activation_dataset.py:499-503)
+                return save_activation_chunk(host if full else host.clone(), chunk_idx, sink.folder)
         else:
             host = src.clone()
 

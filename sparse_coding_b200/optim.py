@@ -2,8 +2,10 @@
 
 The reference passes ``torchopt.adam`` and ``{"lr": …}`` into FunctionalEnsemble (basic_l1_sweep.py:69-73,
 big_sweep_experiments.py:69-79) and lets ``vmap(optimizer.update)`` run ~12 elementwise kernels per leaf. In the
-engine Adam is fused into the weight-gradient epilogue pass (csrc/sce_kernels.cuh: dict_rows_kernel<MODE_ADAM>), so
-on the Python side an optimiser is just its hyper-parameters. ``adam`` mirrors torchopt.adam's keyword names
+engine the whole update of a dictionary row — row-norm Jacobian of the weight gradient, Adam moments and step,
+re-normalisation and the re-split into operand planes for the next step's GEMMs — is ONE streaming kernel that runs
+after the weight-gradient GEMM (csrc/sce_kernels.cuh: dict_rows_kernel<MODE_ADAM>; DESIGN.md §4 explains why it is
+not that GEMM's epilogue), so on the Python side an optimiser is just its hyper-parameters. ``adam`` mirrors torchopt.adam's keyword names
 (``lr, betas, eps, eps_root``; weight decay and the other torchopt options are not supported and raise)."""
 from __future__ import annotations
 

@@ -62,8 +62,39 @@ def gather_rows(chunk: torch.Tensor, idx: Optional[torch.Tensor], sub: Optional[
     return out
 
 
-def _batch_index_lists(sampler) -> Iterable[torch.Tensor]:
-    """Index tensors per batch. For the reference's ``BatchSampler(RandomSampler(range(N)), B, drop_last=False)``
+def _to_device_staged(t: torch.Tensor, device, piece_bytes: int = 64 << 20) -> torch.Tensor:
+    """Host tensor -> device through two pinned staging buffers (asynchronous copies that overlap the host memcpy
+    into the other buffer). A pageable 2 GiB chunk handed to ``tensor.to(device)`` is copied synchronously through
+    the driver's small bounce buffers; the reference does exactly that every batch (its ``pin_memory()`` call
+    discards the result)."""
+    if t.is_cuda:
+        return t
+    if t.is_pinned() or t.numel() * t.element_size() <= piece_bytes:
+        return t.to(device, non_blocking=True)
+    t = t.contiguous()
+    out = torch.empty(t.shape, dtype=t.dtype, device=device)
+    flat_src, flat_dst = t.view(-1), out.view(-1)
+    piece = max(1, piece_bytes // t.element_size())
+    stage = [torch.empty(piece, dtype=t.dtype).pin_memory() for _ in range(2)]
+    done = [None, None]
+    stream = torch.cuda.current_stream(out.device)
+    for k, lo in enumerate(range(0, flat_src.numel(), piece)):
+        hi = min(lo + piece, flat_src.numel())
+        slot = k & 1
+        if done[slot] is not None:
+            done[slot].synchronize()
+        stage[slot][:hi - lo].copy_(flat_src[lo:hi])
+        flat_dst[lo:hi].copy_(stage[slot][:hi - lo], non_blocking=True)
+        done[slot] = torch.cuda.Event()
+        done[slot].record(stream)
+    for ev in done:
+        if ev is not None:
+            ev.synchronize()          # the staging buffers are freed on return
+    return out
+
+
+def _batch_index_lists(sampler, device=None) -> Iterable[torch.Tensor]:
+    """Index tensors per batch (on ``device`` when given). For the reference's ``BatchSampler(RandomSampler(range(N)), B, drop_last=False)``
     (cluster_runs.py:28-32) the permutation is drawn in one go — the same numbers the reference would see, because
     RandomSampler itself draws one ``torch.randperm`` per epoch — instead of building B-element Python lists."""
     inner = getattr(sampler, "sampler", None)
@@ -79,6 +110,8 @@ def _batch_index_lists(sampler) -> Iterable[torch.Tensor]:
         else:
             gen = inner.generator
         perm = torch.randperm(n, generator=gen)
+        if device is not None:
+            perm = perm.to(device, non_blocking=False)      # one upload per chunk; the batches are views of it
         n_full = n // bs * bs
         for i in range(0, n_full, bs):
             yield perm[i:i + bs]
@@ -86,7 +119,8 @@ def _batch_index_lists(sampler) -> Iterable[torch.Tensor]:
             yield perm[n_full:]
         return
     for idxs in sampler:
-        yield torch.as_tensor(idxs, dtype=torch.int64)
+        t = torch.as_tensor(idxs, dtype=torch.int64)
+        yield t if device is None else t.to(device, non_blocking=True)
 
 
 def ensemble_train_loop(ensemble, cfg, args, ensemble_name, sampler, dataset, progress_counter):
@@ -97,11 +131,11 @@ def ensemble_train_loop(ensemble, cfg, args, ensemble_name, sampler, dataset, pr
     device = torch.device(args["device"])
     use_wandb = bool(getattr(cfg, "use_wandb", False))
     run = cfg.wandb_instance if use_wandb else None
-    chunk = dataset if dataset.is_cuda else dataset.to(device, non_blocking=True)
+    chunk = dataset if dataset.is_cuda else _to_device_staged(dataset, device)
     if not chunk.is_contiguous():
         chunk = chunk.contiguous()
-    for i, batch_idxs in enumerate(_batch_index_lists(sampler)):
-        batch = gather_rows(chunk, batch_idxs.to(device, non_blocking=True))
+    for i, batch_idxs in enumerate(_batch_index_lists(sampler, device)):
+        batch = gather_rows(chunk, batch_idxs)
         losses, aux_buffer = ensemble.step_batch(batch)
         if use_wandb:
             num_nonzero = aux_buffer["c"].count_nonzero(dim=-1).float().mean(dim=-1)
@@ -128,10 +162,16 @@ def ensemble_train_loop(ensemble, cfg, args, ensemble_name, sampler, dataset, pr
 
 
 def check_input_range(ensemble) -> None:
-    """Once per chunk (one 4-byte D2H copy): warn when the activations fed to an f16f8 plan leave the range its fp16
-    operand plane holds well (include/sce.h, sce_arith) — the losses would already show inf/NaN for an overflow;
-    very small magnitudes only cost precision, silently."""
+    """Once per chunk (one small D2H copy): read the device-side health flag — a batch beyond the fp16 range or a
+    non-finite loss makes the engine SKIP the affected updates; ``check_health`` then moves an ``arith="auto"``
+    ensemble to bf16x3 (warning) or raises for an explicitly chosen arithmetic — and warn when the activations fed to
+    an f16f8 plan come close to the limits of its fp16 operand plane (very small magnitudes only cost precision,
+    silently)."""
+    if hasattr(ensemble, "check_health"):
+        ensemble.check_health()
     amax = ensemble.input_absmax() if hasattr(ensemble, "input_absmax") else 0.0
+    if hasattr(ensemble, "resolved_arith") and ensemble.resolved_arith() != "f16f8":
+        return
     if amax != amax or amax > 3.0e4 or 0.0 < amax < 1.0e-3:
         import warnings
         warnings.warn(f"largest |activation| fed to the f16f8 arithmetic so far is {amax:g}: outside [1e-3, 3e4]; "
@@ -162,41 +202,77 @@ class ChunkStreamer:
     """Iterates over device-resident chunks. While the caller trains on chunk i, a background thread reads chunk
     i+1 from disk into one of two pinned staging buffers and copies it to one of two HBM buffers on a side stream
     (ping-pong; the copy waits for the compute that last read that HBM buffer). The training stream only waits on
-    the copy-complete event, so disk, host memcpy and H2D all overlap with the GPU work of the previous chunk."""
+    the copy-complete event, so disk, host memcpy and H2D all overlap with the GPU work of the previous chunk.
 
-    def __init__(self, folder: str, order: Iterable[int], device, keep_dtype: bool = True):
+    The file is memory-mapped (``torch.load(mmap=True)``) and copied straight into the pinned buffer: one pass over
+    the bytes on the host instead of unpickle-into-a-new-tensor followed by a second copy.
+
+    ``feed="broadcast"`` (torch.distributed initialised, one process per GPU, every rank streaming the SAME chunk
+    order — the sweep's situation, cluster_runs.py:100-130): only rank ``src`` reads the file and crosses PCIe; the
+    chunk then reaches the other GPUs with one NCCL broadcast over NVLink / NVSwitch on the side stream, issued from
+    the staging thread on a process group of its own. ``feed="per_rank"`` (default): every rank reads and copies for
+    itself (independent PCIe links, no collective)."""
+
+    def __init__(self, folder: str, order: Iterable[int], device, keep_dtype: bool = True, feed: str = "per_rank",
+                 src: int = 0):
         from concurrent.futures import ThreadPoolExecutor
         self.folder, self.order, self.device = folder, list(order), torch.device(device)
         if self.device.index is None:
             self.device = torch.device("cuda", torch.cuda.current_device())
         self.keep_dtype = keep_dtype
+        if feed not in ("per_rank", "broadcast"):
+            raise ValueError("feed must be 'per_rank' or 'broadcast'")
+        self.feed, self.src, self._group = "per_rank", src, None
+        if feed == "broadcast":
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+                self.feed = "broadcast"
+                self._group = dist.new_group()          # collective: every rank constructs its streamer
+                self._rank = dist.get_rank()
         self.copy_stream = torch.cuda.Stream(self.device)
         self._pool = ThreadPoolExecutor(max_workers=1)
         self._pinned = [None, None]
         self._dev = [None, None]
         self._copied = [None, None]     # event: H2D into slot finished (pinned buffer reusable, data visible)
         self._released = [None, None]   # event on the training stream: work reading slot has been enqueued
+        self.stage_seconds = []         # host time of every staging call (disk + pinned copy + enqueue), for reports
 
-    def _stage(self, slot: int, chunk_idx: int):
-        torch.cuda.set_device(self.device)
-        t = torch.load(os.path.join(self.folder, f"{chunk_idx}.pt"), map_location="cpu")
+    def _load(self, chunk_idx: int) -> torch.Tensor:
+        path = os.path.join(self.folder, f"{chunk_idx}.pt")
+        try:
+            t = torch.load(path, map_location="cpu", mmap=True)
+        except (RuntimeError, TypeError, ValueError):            # legacy (non-zip) serialisation cannot be mapped
+            t = torch.load(path, map_location="cpu")
         if not self.keep_dtype or t.dtype not in (torch.float16, torch.float32):
             t = t.float()
-        t = t.contiguous()
-        if self._copied[slot] is not None:
-            self._copied[slot].synchronize()                  # previous copy out of this pinned buffer is done
-        if self._pinned[slot] is None or self._pinned[slot].shape != t.shape or self._pinned[slot].dtype != t.dtype:
-            self._pinned[slot] = torch.empty(t.shape, dtype=t.dtype).pin_memory()
-        self._pinned[slot].copy_(t)
+        return t.contiguous()
+
+    def _stage(self, slot: int, chunk_idx: int):
+        import time
+        t0 = time.perf_counter()
+        torch.cuda.set_device(self.device)
+        t = self._load(chunk_idx)                                 # mapped: shape / dtype known, bytes not read yet
+        reader = self.feed == "per_rank" or self._rank == self.src
         if self._dev[slot] is None or self._dev[slot].shape != t.shape or self._dev[slot].dtype != t.dtype:
             self._dev[slot] = torch.empty(t.shape, dtype=t.dtype, device=self.device)
+        if reader:
+            if self._copied[slot] is not None:
+                self._copied[slot].synchronize()                  # previous copy out of this pinned buffer is done
+            if self._pinned[slot] is None or self._pinned[slot].shape != t.shape or self._pinned[slot].dtype != t.dtype:
+                self._pinned[slot] = torch.empty(t.shape, dtype=t.dtype).pin_memory()
+            self._pinned[slot].copy_(t)
         with torch.cuda.stream(self.copy_stream):
             if self._released[slot] is not None:
                 self.copy_stream.wait_event(self._released[slot])
-            self._dev[slot].copy_(self._pinned[slot], non_blocking=True)
+            if reader:
+                self._dev[slot].copy_(self._pinned[slot], non_blocking=True)
+            if self.feed == "broadcast":
+                import torch.distributed as dist
+                dist.broadcast(self._dev[slot], src=self.src, group=self._group)   # enqueued on copy_stream
             ev = torch.cuda.Event()
             ev.record(self.copy_stream)
         self._copied[slot] = ev
+        self.stage_seconds.append(time.perf_counter() - t0)
         return ev
 
     def __iter__(self):
@@ -215,6 +291,54 @@ class ChunkStreamer:
             self._released[slot] = rel
 
 
+class HostBatchPrefetcher:
+    """Feeds host-resident batches (pinned fp32 / fp16 [B, d] tensors, e.g. what a DataLoader with ``pin_memory``
+    yields) to ``step_batch``: the copy of batch i+1 runs on a side stream while the engine works on batch i, through
+    a small ring of device buffers. Yields device tensors valid until the next iteration."""
+
+    def __init__(self, batches: Iterable[torch.Tensor], device, depth: int = 2):
+        self.batches, self.device, self.depth = batches, torch.device(device), max(2, int(depth))
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.copy_stream = torch.cuda.Stream(self.device)
+
+    def __iter__(self):
+        it = iter(self.batches)
+        main = torch.cuda.current_stream(self.device)
+        bufs, ready, free = [None] * self.depth, [None] * self.depth, [None] * self.depth
+        queue = []
+
+        def issue(slot):
+            try:
+                h = next(it)
+            except StopIteration:
+                return False
+            if bufs[slot] is None or bufs[slot].shape != h.shape or bufs[slot].dtype != h.dtype:
+                bufs[slot] = torch.empty(h.shape, dtype=h.dtype, device=self.device)
+            with torch.cuda.stream(self.copy_stream):
+                if free[slot] is not None:
+                    self.copy_stream.wait_event(free[slot])
+                bufs[slot].copy_(h, non_blocking=True)
+                ready[slot] = torch.cuda.Event()
+                ready[slot].record(self.copy_stream)
+            queue.append(slot)
+            return True
+
+        nxt = 0
+        for _ in range(self.depth - 1):
+            if not issue(nxt % self.depth):
+                break
+            nxt += 1
+        while queue:
+            if issue(nxt % self.depth):
+                nxt += 1
+            slot = queue.pop(0)
+            main.wait_event(ready[slot])
+            yield bufs[slot]
+            free[slot] = torch.cuda.Event()
+            free[slot].record(main)
+
+
 class _Counter:
     value = 0
 
@@ -222,10 +346,11 @@ class _Counter:
 def train_on_chunks(ensemble, args: dict, dataset_folder: str, output_folder: str, batch_size: int,
                     ensemble_hyperparams: List[str], buffer_hyperparams: List[str], n_repetitions: int = 1,
                     center_activations: bool = False, cfg=None, chunk_order: Optional[List[int]] = None,
-                    save_schedule: str = "sweep"):
+                    save_schedule: str = "sweep", feed: str = "per_rank", on_chunk_end=None):
     """The chunk loop of ``sweep`` (big_sweep.py:349-384) / ``basic_l1_sweep`` (basic_l1_sweep.py:85-115) for ONE
     ensemble on ONE GPU, with streamed chunks. Writes ``_{i}/learned_dicts.pt`` (+ ``config.yaml`` when ``cfg`` is
-    given) on the reference's schedule: last chunk, or chunk count in {8, 16, …, 512}."""
+    given) on the reference's schedule: last chunk, or chunk count in {8, 16, …, 512}. ``feed``: see
+    :class:`ChunkStreamer`; ``on_chunk_end(i, chunk_idx, ensemble)`` runs after the last step of every chunk."""
     import yaml
 
     device = torch.device(args["device"])
@@ -238,7 +363,7 @@ def train_on_chunks(ensemble, args: dict, dataset_folder: str, output_folder: st
     means = None
     cfg = cfg if cfg is not None else type("Cfg", (), {"use_wandb": False})()
     learned_dicts = []
-    for i, (chunk_idx, chunk) in enumerate(ChunkStreamer(dataset_folder, chunk_order, device)):
+    for i, (chunk_idx, chunk) in enumerate(ChunkStreamer(dataset_folder, chunk_order, device, feed=feed)):
         if center_activations:
             if means is None:
                 means = chunk.float().mean(dim=0)
@@ -249,9 +374,12 @@ def train_on_chunks(ensemble, args: dict, dataset_folder: str, output_folder: st
         torch.set_grad_enabled(False)
         torch.manual_seed(0)
         np.random.seed(0)
-        for j, idx in enumerate(_batch_index_lists(sampler)):
-            batch = gather_rows(chunk, idx.to(device, non_blocking=True), sub=means)
+        for j, idx in enumerate(_batch_index_lists(sampler, device)):
+            batch = gather_rows(chunk, idx, sub=means)
             ensemble.step_batch(batch)
+        check_input_range(ensemble)
+        if on_chunk_end is not None:
+            on_chunk_end(i, chunk_idx, ensemble)      # e.g. the end-of-chunk metric gather (sharding.gather_metrics)
         last = i == len(chunk_order) - 1
         if last or (save_schedule == "sweep" and (i + 1) in [2 ** j for j in range(3, 10)]) or save_schedule == "every":
             # export (a full D2H of the parameters, which also drains the GPU) only when a checkpoint is due
@@ -275,10 +403,12 @@ def train_on_chunks(ensemble, args: dict, dataset_folder: str, output_folder: st
 def save_resume_state(ensemble, path: str) -> None:
     sd = ensemble.state_dict()
     cpu = lambda tree: {k: (cpu(v) if isinstance(v, dict) else v.detach().cpu()) for k, v in tree.items()}
-    torch.save({"params": cpu(sd["params"]), "buffers": cpu(sd["buffers"]), "optim_states": cpu(sd["optim_states"]),
-                "sig": sd["sig"], "optimizer_kwargs": sd["optimizer_kwargs"], "n_models": sd["n_models"],
-                "adam_count_mode": sd["adam_count_mode"], "fwd_passes": sd["fwd_passes"],
-                "bwd_passes": sd["bwd_passes"], "steps": sd["steps"], "no_stacking": sd["no_stacking"]}, path)
+    blob = {"params": cpu(sd["params"]), "buffers": cpu(sd["buffers"]), "optim_states": cpu(sd["optim_states"])}
+    # every other key of state_dict() — the reference's (sig, optimizer_kwargs, n_models, no_stacking) and all
+    # engine-only settings (adam_count_mode, passes, arith and a bf16x3 fall-back taken earlier, health interval,
+    # materialize_code, steps) — so that a resumed run computes exactly as the saved one did
+    blob.update({k: v for k, v in sd.items() if k not in ("params", "buffers", "optim_states", "device", "optimizer_func")})
+    torch.save(blob, path)
 
 
 def load_resume_state(path: str, device):
@@ -288,5 +418,5 @@ def load_resume_state(path: str, device):
     dev = lambda tree: {k: (dev(v) if isinstance(v, dict) else v.to(device)) for k, v in tree.items()}
     sd = dict(blob)
     sd.update(device=device, params=dev(blob["params"]), buffers=dev(blob["buffers"]),
-              optim_states=dev(blob["optim_states"]), optimizer_func=adam, materialize_code=False)
+              optim_states=dev(blob["optim_states"]), optimizer_func=adam)
     return FunctionalEnsemble.from_state(sd)

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     lib = _lib.load()
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.sce_version() == 101
+    assert lib.sce_version() == 200
 
 
 def test_abi_validation_without_device():
@@ -212,3 +212,41 @@ def test_batch_index_lists_follow_the_reference_sampler():
     torch.manual_seed(0)
     again = [t.tolist() for t in _batch_index_lists(mk())]
     assert again == ref                                             # Q7: same shuffle after re-seeding
+
+
+def test_resume_state_keeps_engine_settings(tmp_path):
+    """save_resume_state / load_resume_state carry every engine-only setting: a run pinned to arith='bf16x3' (its
+    activations leave the fp16 range) must not silently resume on the narrower f16f8 arithmetic, and a bf16x3
+    fall-back taken by an 'auto' plan sticks as well."""
+    from sparse_coding_b200.train_loop import load_resume_state, save_resume_state
+    torch.manual_seed(0)
+    models = [S.FunctionalTiedSAE.init(16, 32, a) for a in (1e-3, 1e-2)]
+    ens = S.FunctionalEnsemble(models, S.FunctionalTiedSAE, S.adam, {"lr": 2e-3}, device="cpu", arith="bf16x3",
+                               adam_count_mode="standard", bwd_passes=1, health_check_every=5)
+    ens._steps = 7
+    save_resume_state(ens, str(tmp_path / "a.pt"))
+    back = load_resume_state(str(tmp_path / "a.pt"), "cpu")
+    assert (back.arith, back.adam_count_mode, back.bwd_passes, back.fwd_passes) == ("bf16x3", "standard", 1, 3)
+    assert back._steps == 7 and back.health_check_every == 5 and back.optimizer.lr == pytest.approx(2e-3)
+    assert back._arith_fallback is None
+    auto = S.FunctionalEnsemble(models, S.FunctionalTiedSAE, S.adam, {"lr": 1e-3}, device="cpu")
+    auto._arith_fallback = "bf16x3"                     # what check_health() records after an fp16 overflow
+    save_resume_state(auto, str(tmp_path / "b.pt"))
+    back = load_resume_state(str(tmp_path / "b.pt"), "cpu")
+    assert back.arith == "auto" and back._arith_fallback == "bf16x3"
+
+
+def test_from_state_continues_the_step_count_of_a_dead_worker():
+    """cluster_runs.py:113-125: the parent hands state_dict() to a freshly spawned worker per chunk; the worker's
+    Python-side step counter dies with it, but optim_states['count'] is shared memory updated in place — with
+    adam_count_mode='standard' the next worker continues the bias correction from there."""
+    torch.manual_seed(0)
+    models = [S.FunctionalTiedSAE.init(16, 32, 1e-3) for _ in range(2)]
+    ens = S.FunctionalEnsemble(models, S.FunctionalTiedSAE, S.adam, {"lr": 1e-3}, device="cpu",
+                               adam_count_mode="standard")
+    sd = ens.state_dict()                               # the parent's view: steps == 0 for ever
+    for t in ens.optim_states["count"].values():
+        t.add_(12)                                      # what 12 steps of a child did to the shared tensors
+    assert S.FunctionalEnsemble.from_state(sd)._steps == 12
+    frozen = S.FunctionalEnsemble(models, S.FunctionalTiedSAE, S.adam, {"lr": 1e-3}, device="cpu")
+    assert S.FunctionalEnsemble.from_state(frozen.state_dict())._steps == 0
