@@ -143,12 +143,14 @@ def tied_grads(E, b, X, alpha, bias_decay=0.0, coef_mask=None, active=None) -> D
     return f
 
 
-def untied_grads(E, b, D, X, alpha, bias_decay=0.0, coef_mask=None) -> Dict[str, Tensor]:
+def untied_grads(E, b, D, X, alpha, bias_decay=0.0, coef_mask=None, active=None) -> Dict[str, Tensor]:
+    """``active``: as in :func:`tied_grads` (pins the ReLU activity pattern of near-kink coefficients)."""
     f = untied_forward(E, b, D, X, alpha, bias_decay, coef_mask)
     B, d = X.shape
     G = 2.0 * (f["x_hat"] - X) / (B * d)
-    dC = G @ f["W"].T + (alpha / B) * (f["c"] > 0).to(X.dtype)
-    gate = f["Z"] >= 0
+    pos = (f["c"] > 0) if active is None else active
+    dC = G @ f["W"].T + (alpha / B) * pos.to(X.dtype)
+    gate = (f["Z"] >= 0) if active is None else (active | (f["Z"] == 0))
     if coef_mask is not None:
         gate = gate & ~coef_mask
     dZ = dC * gate.to(X.dtype)
@@ -160,9 +162,17 @@ def untied_grads(E, b, D, X, alpha, bias_decay=0.0, coef_mask=None) -> Dict[str,
     return f
 
 
-def topk_grads(Dct, X, k) -> Dict[str, Tensor]:
+def topk_grads(Dct, X, k, support=None) -> Dict[str, Tensor]:
+    """``support`` (bool [B, n], optional) replaces the oracle's own selection-and-positive pattern: torch.topk
+    leaves ties unspecified and a k-th score within rounding of the (k+1)-th may be ranked differently
+    by two precisions, so a checker comparing them pins the support and separately verifies that it is a valid top-k."""
     f = topk_forward(Dct, X, k)
     B, d = X.shape
+    if support is not None:
+        f["c"] = torch.where(support, f["Z"], torch.zeros_like(f["Z"])).clamp(min=0.0)
+        f["sel"] = support
+        f["x_hat"] = f["c"] @ f["W"]
+        f["loss"] = (X - f["x_hat"]).pow(2).mean()
     G = 2.0 * (f["x_hat"] - X) / (B * d)
     dS = (G @ f["W"].T) * (f["sel"] & (f["Z"] > 0)).to(X.dtype)   # relu: zero gradient at exactly 0
     dW = dS.T @ X + f["c"].T @ G

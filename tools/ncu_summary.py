@@ -53,5 +53,24 @@ def full(path):
                 print(f"    {m:70s} {row[idx[m]]:>14s} {units[idx[m]]}")
 
 
+def traffic(path):
+    """DRAM bytes (read + write) of the LAST captured launch of every distinct kernel, and their sum = bytes per step
+    when the capture covers one step: the numbers profiles/ncu_traffic.json carries for bench.py's roofline."""
+    import json
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    idx = {h: i for i, h in enumerate(hdr)}
+    scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+    per = {}
+    for row in rows[2:]:
+        name = row[idx["Kernel Name"]][:120]
+        b = 0.0
+        for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            b += float(row[idx[m]].replace(",", "")) * scale.get(units[idx[m]], 1.0)
+        per[name] = b
+    print(json.dumps({"dram_bytes_per_kernel": per, "dram_bytes_per_step": sum(per.values())}, indent=1))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](sys.argv[2])
