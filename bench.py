@@ -363,6 +363,23 @@ def run_stream(S, dist, rank, world, dev, M, d, n, B, n_chunks, rows, feed, resi
             return losses, aux
 
         ens.step_batch = step_and_keep
+        # the same number of steps from ONE device-resident chunk first (same gather + step code path, nothing
+        # streamed): an equally long, equally power-limited run to compare the streamed one with, and its warm-up
+        from sparse_coding_b200.train_loop import gather_rows
+        steps_per_chunk = (rows + B - 1) // B
+        res_chunk = torch.load(os.path.join(folder, "0.pt"), map_location="cpu", mmap=True).to(dev)
+        perm = torch.randperm(rows, device=dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for c in range(n_chunks):
+            for j in range(steps_per_chunk):
+                ens.step_batch(gather_rows(res_chunk, perm[j * B:(j + 1) * B]))
+            on_chunk_end(c, 0, ens)
+        t_res = time.perf_counter() - t0
+        del res_chunk, perm
+        marks.clear()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -373,11 +390,11 @@ def run_stream(S, dist, rank, world, dev, M, d, n, B, n_chunks, rows, feed, resi
         torch.cuda.synchronize()
         t_all = time.perf_counter()
         t_train = marks[-1][0] - t0
-        steps_per_chunk = (rows + B - 1) // B
-        t = torch.tensor([t_train, t_all - marks[-1][0], marks[-1][0] - marks[0][0]], device=dev, dtype=torch.float64)
+        t = torch.tensor([t_train, t_all - marks[-1][0], marks[-1][0] - marks[0][0], t_res], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        t_train, t_export, t_steady = float(t[0]), float(t[1]), float(t[2])
+        t_train, t_export, t_steady, t_res = float(t[0]), float(t[1]), float(t[2]), float(t[3])
+        chunk_seconds = [marks[0][0] - t0] + [marks[i][0] - marks[i - 1][0] for i in range(1, len(marks))]
         total_rows = n_chunks * rows
         out = {
             "value": world * total_rows / t_train, "unit": "activations/s",
@@ -386,7 +403,12 @@ def run_stream(S, dist, rank, world, dev, M, d, n, B, n_chunks, rows, feed, resi
             "ms_per_step": t_train / (n_chunks * steps_per_chunk) * 1e3,
             # chunks 1.. only: the first chunk's load is not hidden behind anything
             "steady_ms_per_step": (t_steady / ((n_chunks - 1) * steps_per_chunk) * 1e3) if n_chunks > 1 else None,
-            "export_seconds": t_export, "metric_gather_rows": marks[-1][1],
+            "export_seconds": t_export, "metric_gather_rows": marks[-1][1], "chunk_seconds": chunk_seconds,
+            "resident_chunk_ms_per_step": t_res / (n_chunks * steps_per_chunk) * 1e3,
+            "vs_resident_chunk": (t_res / n_chunks) / (t_steady / (n_chunks - 1)) if n_chunks > 1 else None,
+            "vs_resident_chunk_note": "steady-state streamed chunk time against an equally long run of the same gather + "
+                                      "step loop over ONE device-resident chunk (equal power / clock conditions); "
+                                      "vs_resident_pool compares with the short `value` burst instead",
             "includes": "torch.load(mmap) + pinned copy + H2D on a side stream, device-side permutation gather with "
                         "fp16->fp32, step, end-of-chunk all_gather of per-model metrics; excludes chunk synthesis and "
                         "the final learned_dicts.pt export (export_seconds)",

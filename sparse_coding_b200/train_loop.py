@@ -93,8 +93,14 @@ def _to_device_staged(t: torch.Tensor, device, piece_bytes: int = 64 << 20) -> t
     return out
 
 
-def _batch_index_lists(sampler, device=None) -> Iterable[torch.Tensor]:
-    """Index tensors per batch (on ``device`` when given). For the reference's ``BatchSampler(RandomSampler(range(N)), B, drop_last=False)``
+_PERM_CACHE: dict = {}      # (rows, seed, device) -> permutation on the device; see _batch_index_lists
+
+
+def _batch_index_lists(sampler, device=None, perm_cache: Optional[dict] = None) -> Iterable[torch.Tensor]:
+    """Index tensors per batch (on ``device`` when given). ``perm_cache``: the reference re-seeds the global RNG at
+    the start of every chunk (big_sweep.py:161), so equal-length chunks draw the SAME sampler seed and hence the same
+    permutation; keyed by (rows, that seed, device) the 2M-element randperm and its upload are done once
+    instead of once per chunk — the numbers are identical either way. For the reference's ``BatchSampler(RandomSampler(range(N)), B, drop_last=False)``
     (cluster_runs.py:28-32) the permutation is drawn in one go — the same numbers the reference would see, because
     RandomSampler itself draws one ``torch.randperm`` per epoch — instead of building B-element Python lists."""
     inner = getattr(sampler, "sampler", None)
@@ -105,13 +111,21 @@ def _batch_index_lists(sampler, device=None) -> Iterable[torch.Tensor]:
         # global RNG (or use the sampler's own), draw one permutation
         n = len(inner.data_source)
         if inner.generator is None:
+            seed = int(torch.empty((), dtype=torch.int64).random_().item())
+            key = (n, seed, str(device))
             gen = torch.Generator()
-            gen.manual_seed(int(torch.empty((), dtype=torch.int64).random_().item()))
+            gen.manual_seed(seed)
         else:
-            gen = inner.generator
-        perm = torch.randperm(n, generator=gen)
-        if device is not None:
-            perm = perm.to(device, non_blocking=False)      # one upload per chunk; the batches are views of it
+            gen, key = inner.generator, None
+        perm = perm_cache.get(key) if (perm_cache is not None and key is not None) else None
+        if perm is None:
+            perm = torch.randperm(n, generator=gen)
+            if device is not None:
+                perm = perm.to(device, non_blocking=False)  # one upload per chunk; the batches are views of it
+            if perm_cache is not None and key is not None:
+                if len(perm_cache) >= 4:
+                    perm_cache.clear()
+                perm_cache[key] = perm
         n_full = n // bs * bs
         for i in range(0, n_full, bs):
             yield perm[i:i + bs]
@@ -134,7 +148,7 @@ def ensemble_train_loop(ensemble, cfg, args, ensemble_name, sampler, dataset, pr
     chunk = dataset if dataset.is_cuda else _to_device_staged(dataset, device)
     if not chunk.is_contiguous():
         chunk = chunk.contiguous()
-    for i, batch_idxs in enumerate(_batch_index_lists(sampler, device)):
+    for i, batch_idxs in enumerate(_batch_index_lists(sampler, device, _PERM_CACHE)):
         batch = gather_rows(chunk, batch_idxs)
         losses, aux_buffer = ensemble.step_batch(batch)
         if use_wandb:
@@ -363,6 +377,7 @@ def train_on_chunks(ensemble, args: dict, dataset_folder: str, output_folder: st
     means = None
     cfg = cfg if cfg is not None else type("Cfg", (), {"use_wandb": False})()
     learned_dicts = []
+    perm_cache: dict = {}
     for i, (chunk_idx, chunk) in enumerate(ChunkStreamer(dataset_folder, chunk_order, device, feed=feed)):
         if center_activations:
             if means is None:
@@ -374,7 +389,7 @@ def train_on_chunks(ensemble, args: dict, dataset_folder: str, output_folder: st
         torch.set_grad_enabled(False)
         torch.manual_seed(0)
         np.random.seed(0)
-        for j, idx in enumerate(_batch_index_lists(sampler, device)):
+        for j, idx in enumerate(_batch_index_lists(sampler, device, perm_cache)):
             batch = gather_rows(chunk, idx, sub=means)
             ensemble.step_batch(batch)
         check_input_range(ensemble)
