@@ -70,6 +70,8 @@ typedef struct sce_desc {
   int bwd_passes;       /* same for the three backward GEMMs */
   float norm_floor;     /* clamp floor of the row norms: 1e-8 (SAE variants); <= 0 disables it (TopK) */
   int arith;            /* enum sce_arith; 0 = AUTO */
+  int topk_k_max;       /* SCE_TOPK: the largest buffers["sparsity"] of the ensemble (1..256) enables the k-sparse decode /
+                           code-gradient kernels; 0 = unknown: dense GEMMs on the k-sparse code, as the reference does */
 } sce_desc;
 
 /* Device pointers owned by the caller; all fp32 unless noted. Unused ones are NULL. */

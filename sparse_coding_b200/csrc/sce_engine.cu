@@ -9,6 +9,8 @@
 //   GEMM dcode      dz = (g W^T + alpha/B [c>0]) [z>=0] -> (dz_hi, dz_lo), db partials
 //   GEMM dW         dW = dz^T x + c^T g                                            [M x n x d, K = 2B]
 //   bias_norm, finalize (losses), dict_rows<ADAM> (Jacobian + Adam + renormalise + re-split), bias<ADAM>
+// Top-k variant: the encode GEMM stores fp32 scores; topk_select2_kernel keeps k per row; with the k-sparse path
+// (sce_topk.cuh) decode and dcode are a gather kernel over the k selected dictionary rows instead of two dense GEMMs.
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -20,6 +22,7 @@
 #include "sce_epilogues.cuh"
 #include "sce_gemm.cuh"
 #include "sce_kernels.cuh"
+#include "sce_topk.cuh"
 #include "sce_tmap.h"
 
 using namespace sce;
@@ -72,6 +75,13 @@ struct sce_plan {
   __nv_bfloat16 *g_hi, *g_lo;     // [M, Bmax, d]
   __nv_bfloat16 *dz_hi, *dz_lo;   // [M, Bmax, n]   (top-k: fp32 scores alias these planes)
   uint8_t *x_x8, *wenc_x8, *wdec_x8, *c_x8, *g_x8, *dz_x8;
+  float* scores;                  // top-k: fp32 scores [M, Bmax, n] of the encode GEMM
+  int *tk_col, *tk_cnt;           // top-k lists (TopkLists): selected columns [M, Bmax, kmax], entries per row [M, Bmax]
+  float *tk_val, *tk_dots;        // their values [M, Bmax, kmax]; per-slice shares of g . W_j [M, Bmax, kmax, slices]
+  float* wn_f32;                  // top-k: fp32 copy of the normalised dictionary [M, n, d] the gather kernel reads
+  int tk_slices;                  // slices of the activation width topk_sparse_kernel runs per row
+  int tk_kmax;                    // list capacity per row (desc.topk_k_max rounded up to 8; 0: no lists)
+  int topk_sparse;                // 1: decode / dcode of the top-k variant run as the k-sparse gather kernels
   uint32_t *act_pos, *act_zero;   // activity masks [M][ceil(n/32)][Bmax]: bit 31-j of a word = column 32*chunk + j (ActMask)
   uint32_t* res_flags;            // [0]: the batch has a non-zero residual plane (f16f8; written by the batch split)
   float *dw_enc, *dw_dec;         // [M, n, d]
@@ -142,6 +152,30 @@ static int resolve_arith(const sce_desc& d) {
   return shape_ok ? kArithF16F8 : kArithBf16x3;
 }
 
+// capacity per row of the top-k lists: the largest k of the ensemble (desc.topk_k_max, supplied by the host mirror, which
+// knows buffers["sparsity"]) rounded up to 8; 0 = unknown or too large for the gather kernel -> dense path, no lists
+static size_t topk_kmax(const sce_desc& d) {
+  if (d.variant != SCE_TOPK || d.topk_k_max < 1 || d.topk_k_max > 256) return 0;
+  return (size_t)(d.topk_k_max + 7) / 8 * 8;
+}
+// topk_sparse_kernel: dynamic shared memory for `slices` slices of the activation width (see there), and the slice
+// count a plan uses: the smallest of 2, 4, 8 whose slice fits (two blocks per SM); 0 when none does (the plan then runs
+// the dense GEMMs)
+constexpr int kTopkMaxSlices = 8;
+static size_t topk_sparse_smem(const sce_desc& d, size_t kmax, int slices) {
+  const size_t ds = d.d / slices;
+  return kmax * ds * sizeof(float) + 9 * ds * sizeof(float) + kmax * 8 + 128;
+}
+static int topk_slices(const sce_desc& d, size_t kmax) {
+  int best = 0;
+  for (int s = 2; s <= kTopkMaxSlices; s *= 2) {
+    if (d.d % (4 * s) || d.d / s > 512) continue;
+    const size_t b = topk_sparse_smem(d, kmax, s);
+    if (b <= 112 * 1024) return s;   // fewest slices that fit: the kernel's time goes with the number of blocks
+  }
+  return best;
+}
+
 // Carves the workspace; with base == nullptr only measures it.
 static size_t carve(sce_plan* p, const sce_desc& d, uint8_t* base) {
   Carve c{base, 0};
@@ -178,7 +212,8 @@ static size_t carve(sce_plan* p, const sce_desc& d, uint8_t* base) {
   if (d.variant == SCE_UNTIED) dwd = c.take<float>(M * n * dd);
   const size_t enc_parts = d.variant == SCE_TOPK ? B : tiles_mB * 8 * tiles_nN;
   auto pe = c.take<float>(M * enc_parts * 2);
-  auto pd = c.take<float>(M * tiles_mB * 8 * tiles_nD);
+  const size_t dec_parts = tiles_mB * 8 * tiles_nD;   // top-k: up to kTopkMaxSlices partials per row from the gather kernel
+  auto pd = c.take<float>(M * (d.variant == SCE_TOPK && dec_parts < kTopkMaxSlices * B ? kTopkMaxSlices * B : dec_parts));
   auto dbp = c.take<float>(M * tiles_mB * 4 * n);
   auto bn = c.take<float>(M);
   auto lob = c.take<float>(M);
@@ -187,6 +222,21 @@ static size_t carve(sce_plan* p, const sce_desc& d, uint8_t* base) {
   const size_t n_chunks = (n + 31) / 32;
   auto apos = c.take<uint32_t>(M * n_chunks * B);
   auto azero = c.take<uint32_t>(M * n_chunks * B);
+  // top-k: scores of their own (the code-gradient planes must keep their scattered zeros) and the k-sparse lists
+  const size_t kmax = topk_kmax(d);
+  float* sc = nullptr;
+  int *tkc = nullptr, *tkn = nullptr;
+  float *tkv = nullptr, *tkd = nullptr, *wnf = nullptr;
+  if (d.variant == SCE_TOPK) {
+    sc = c.take<float>(M * B * n);
+    if (kmax) {
+      tkc = c.take<int>(M * B * kmax);
+      tkv = c.take<float>(M * B * kmax);
+      tkn = c.take<int>(M * B);
+      tkd = c.take<float>(M * B * kmax * kTopkMaxSlices);
+      wnf = c.take<float>(M * n * dd);
+    }
+  }
   auto rf = c.take<uint32_t>(kFlagWords);   // [0] residual flag, [kAbsmaxWord] input range monitor, [kBadWord] health (separate 128-byte lines)
   if (p) {
     p->x_stage = X;
@@ -218,6 +268,13 @@ static size_t carve(sce_plan* p, const sce_desc& d, uint8_t* base) {
     p->loss_stage = ls;
     p->nnz_stage = ns;
     p->res_flags = rf;
+    p->scores = sc;
+    p->tk_col = tkc;
+    p->tk_val = tkv;
+    p->tk_cnt = tkn;
+    p->tk_dots = tkd;
+    p->wn_f32 = wnf;
+    p->tk_kmax = (int)kmax;
     p->act_pos = apos;
     p->act_zero = azero;
     p->tiles_mB_max = (int)tiles_mB;
@@ -483,14 +540,14 @@ static AdamHyper hyper_for(const sce_plan* p, long long t) {
 template <int MODE, int ARITH>
 static int launch_dict_rows_t(float* e, const float* dw, float* m, float* v, void* hi, void* lo, void* x8,
                               float* grad_out, long long rows, int d, int normalize, float floor, AdamHyper h,
-                              const uint32_t* health, cudaStream_t st) {
+                              const uint32_t* health, float* w_f32, cudaStream_t st) {
   const int nv = (d + 511) / 512;
   if (nv == 1)
-    dict_rows_kernel<1, MODE, ARITH><<<(unsigned)rows, 128, 0, st>>>(e, dw, m, v, hi, lo, x8, grad_out, d, normalize, floor, h, health);
+    dict_rows_kernel<1, MODE, ARITH><<<(unsigned)rows, 128, 0, st>>>(e, dw, m, v, hi, lo, x8, grad_out, d, normalize, floor, h, health, w_f32);
   else if (nv == 2)
-    dict_rows_kernel<2, MODE, ARITH><<<(unsigned)rows, 128, 0, st>>>(e, dw, m, v, hi, lo, x8, grad_out, d, normalize, floor, h, health);
+    dict_rows_kernel<2, MODE, ARITH><<<(unsigned)rows, 128, 0, st>>>(e, dw, m, v, hi, lo, x8, grad_out, d, normalize, floor, h, health, w_f32);
   else
-    dict_rows_kernel<4, MODE, ARITH><<<(unsigned)rows, 128, 0, st>>>(e, dw, m, v, hi, lo, x8, grad_out, d, normalize, floor, h, health);
+    dict_rows_kernel<4, MODE, ARITH><<<(unsigned)rows, 128, 0, st>>>(e, dw, m, v, hi, lo, x8, grad_out, d, normalize, floor, h, health, w_f32);
   CUDA_TRY(cudaGetLastError());
   return SCE_OK;
 }
@@ -502,9 +559,10 @@ static int launch_dict_rows(const sce_plan* p, int which, float* e, const float*
   void* lo = which ? (void*)p->wdec_lo : (void*)p->wenc_lo;
   void* x8 = which ? (void*)p->wdec_x8 : (void*)p->wenc_x8;
   if (MODE == MODE_GRAD) hi = lo = x8 = nullptr;
+  float* wf = (MODE != MODE_GRAD && p->topk_sparse) ? p->wn_f32 : nullptr;   // (top-k plans have one dictionary)
   return p->arith == kArithF16F8
-             ? launch_dict_rows_t<MODE, kArithF16F8>(e, dw, m, v, hi, lo, x8, grad_out, rows, d, normalize, floor, h, p->res_flags, st)
-             : launch_dict_rows_t<MODE, kArithBf16x3>(e, dw, m, v, hi, lo, x8, grad_out, rows, d, normalize, floor, h, p->res_flags, st);
+             ? launch_dict_rows_t<MODE, kArithF16F8>(e, dw, m, v, hi, lo, x8, grad_out, rows, d, normalize, floor, h, p->res_flags, wf, st)
+             : launch_dict_rows_t<MODE, kArithBf16x3>(e, dw, m, v, hi, lo, x8, grad_out, rows, d, normalize, floor, h, p->res_flags, wf, st);
 }
 
 // f16f8 runs the backward pass on the residual r instead of g = 2r/(B d) (EpiDecodeT): weight- and bias-gradient
@@ -574,6 +632,7 @@ static int run_pipeline_t(sce_plan* p, const float* x, int B, float* x_hat, bool
   // ---- encode
   prof_mark(p, SCE_PHASE_ENCODE, st);
   int n_enc_parts;
+  TopkLists tk = {nullptr, nullptr, nullptr, 0, 0};
   if (d.variant != SCE_TOPK) {
     typename EpiEnc::Params ep;
     ep.out_hi = maps->st_c_hi;
@@ -592,9 +651,9 @@ static int run_pipeline_t(sce_plan* p, const float* x, int B, float* x_hat, bool
     ++launches;
     n_enc_parts = tiles_mB * 8 * ep.tiles_n;
   } else {
-    // scores -> fp32 (aliasing the dz pair), then per-row selection
+    // scores -> fp32, then per-row selection (code planes, activity mask, k-sparse lists)
     EpiStoreF32::Params sp;
-    sp.out = reinterpret_cast<float*>(p->dz_hi);
+    sp.out = p->scores;
     sp.model_stride = Bm * n;
     sp.ld = n;
     sp.scale = 1.f;
@@ -603,23 +662,39 @@ static int run_pipeline_t(sce_plan* p, const float* x, int B, float* x_hat, bool
     if (rc) return rc;
     ++launches;
     if ((size_t)n * 4 > 200 * 1024) return fail(SCE_ERR_INVALID, "top-k: n = %d exceeds the shared-memory row buffer", n);
-    const int use_cand = (size_t)n * 8 <= 200 * 1024;   // keys + candidate list, else keys only
     static bool cfg[64] = {};
     if (p->device < 0 || p->device >= 64 || !cfg[p->device]) {
-      CUDA_TRY(cudaFuncSetAttribute(topk_select_kernel<AR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      CUDA_TRY(cudaFuncSetAttribute(topk_select2_kernel<AR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      CUDA_TRY(cudaFuncSetAttribute(topk_sparse_kernel<AR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
       if (p->device >= 0 && p->device < 64) cfg[p->device] = true;
     }
+    tk.col = p->tk_col;
+    tk.val = p->tk_val;
+    tk.cnt = p->tk_cnt;
+    tk.kmax = p->tk_kmax;
+    tk.batch_max = d.batch_max;
     // one block per (row, model); scores / codes of model m start at m * batch_max * n
-    topk_select_kernel<AR><<<dim3(B, M), 256, (size_t)n * (use_cand ? 8 : 4), st>>>(
-        reinterpret_cast<const float*>(p->dz_hi), p->b.sparsity, p->c_hi, p->c_lo, p->c_x8, act, p->part_enc, B, n, Bm * n,
-        use_cand);
+    topk_select2_kernel<AR><<<dim3(B, M), 256, (size_t)n * 4, st>>>(p->scores, p->b.sparsity, p->c_hi, p->c_lo, p->c_x8, act,
+                                                                     tk, p->part_enc, B, n, Bm * n);
     ++launches;
     CUDA_TRY(cudaGetLastError());
     n_enc_parts = B;
   }
 
-  // ---- decode (+ residual, loss partial, g)
+  const bool sparse = d.variant == SCE_TOPK && p->topk_sparse;
+  int n_dec_parts;
   prof_mark(p, SCE_PHASE_DECODE, st);
+  if (sparse) {
+    // ---- k-sparse decode + residual + loss partial + g planes + the code gradient at the selected entries
+    const float gscale = f8 ? 1.0f : 2.0f / ((float)B * (float)dd);
+    topk_sparse_kernel<AR><<<dim3(B, M, p->tk_slices), 256, topk_sparse_smem(d, p->tk_kmax, p->tk_slices), st>>>(
+        tk, p->b.sparsity, p->wn_f32, x, d.x_per_model ? (long long)B * dd : 0, p->g_hi, p->g_lo, p->g_x8, x_hat, p->part_dec,
+        backward ? p->tk_dots : nullptr, B, n, dd, gscale);
+    ++launches;
+    CUDA_TRY(cudaGetLastError());
+    n_dec_parts = p->tk_slices * B;
+  } else {
+  // ---- decode (+ residual, loss partial, g)
   typename EpiDec::Params dp;
   dp.x = x;
   dp.x_model_stride = d.x_per_model ? (long long)B * dd : 0;
@@ -642,6 +717,8 @@ static int run_pipeline_t(sce_plan* p, const float* x, int B, float* x_hat, bool
                                            n, d.fwd_passes, B, dd, dp, st);
   if (rc) return rc;
   ++launches;
+  n_dec_parts = tiles_mB * 8 * dp.tiles_n;
+  }
 
   // ---- losses
   prof_mark(p, SCE_PHASE_LOSSES, st);
@@ -649,7 +726,7 @@ static int run_pipeline_t(sce_plan* p, const float* x, int B, float* x_hat, bool
     bias_norm_kernel<<<M, 256, 0, st>>>(p->b.encoder_bias, n, p->bnorm);
     ++launches;
   }
-  finalize_kernel<<<M, 256, 0, st>>>(p->part_enc, n_enc_parts, p->part_dec, tiles_mB * 8 * dp.tiles_n, p->b.l1_alpha,
+  finalize_kernel<<<M, 256, 0, st>>>(p->part_enc, n_enc_parts, p->part_dec, n_dec_parts, p->b.l1_alpha,
                                      p->b.encoder_bias ? p->b.bias_decay : nullptr, p->bnorm, B, dd, out_losses, out_nnz,
                                      p->res_flags);
   ++launches;
@@ -657,6 +734,12 @@ static int run_pipeline_t(sce_plan* p, const float* x, int B, float* x_hat, bool
 
   prof_mark(p, SCE_PHASE_DCODE, st);
   if (backward) {
+    if (sparse) {
+      // ---- code gradient planes: zero the rows, scatter the k entries
+      topk_dz_scatter_kernel<AR><<<dim3(B, M), 256, 0, st>>>(tk, p->tk_dots, p->tk_slices, p->dz_hi, p->dz_lo, p->dz_x8, n);
+      ++launches;
+      CUDA_TRY(cudaGetLastError());
+    } else {
     // ---- dcode
     typename EpiDco::Params zp;
     zp.out_hi = maps->st_dz_hi;
@@ -670,6 +753,7 @@ static int run_pipeline_t(sce_plan* p, const float* x, int B, float* x_hat, bool
                                             p->dcode_passes, B, n, zp, st);
     if (rc) return rc;
     ++launches;
+    }
 
     // ---- weight gradients
     prof_mark(p, SCE_PHASE_DW, st);
@@ -792,6 +876,24 @@ int sce_plan_create(const sce_desc* desc, const sce_buffers* buffers, sce_plan**
   p->bk_encode = tune_bk("SCE_TUNE_BK_ENCODE", 64);
   p->bk_decode = tune_bk("SCE_TUNE_BK_DECODE", 32);
   p->bk_dcode = tune_bk("SCE_TUNE_BK_DCODE", 64);
+  {
+    // k-sparse decode / dcode of the top-k variant: lists known (topk_k_max), bulk-copy alignment of the dictionary
+    // half rows (16 bytes in every plane), shared memory of the gather kernel
+    const size_t kmax = topk_kmax(*desc);
+    p->tk_slices = kmax ? topk_slices(*desc, kmax) : 0;
+    if (const char* v = getenv("SCE_TOPK_SLICES")) {
+      const int sl = atoi(v);
+      if (kmax && (sl == 2 || sl == 4 || sl == 8) && desc->d % (4 * sl) == 0 && desc->d / sl <= 512 &&
+          topk_sparse_smem(*desc, kmax, sl) <= 112 * 1024)
+        p->tk_slices = sl;
+    }
+    // Worth it where the dictionary is large against k: the dense decode + dcode GEMMs cost ~ n per row, the gather
+    // kernel ~ k (it is bound by the latency chain of a block, not by bytes). Measured on B200 (profiles/r02d_topk_*):
+    // d = 768, 12 models, k in {16, 32, 64}: n = 6144 dense 2.9 ms / sparse 3.7 ms, n = 12288 dense 5.8 ms / sparse 3.7 ms.
+    // SCE_TOPK_SPARSE = 1 / 0 forces it on / off.
+    const int heuristic = (long long)desc->n >= 160ll * (long long)(kmax ? kmax : 1);
+    p->topk_sparse = desc->variant == SCE_TOPK && kmax > 0 && p->tk_slices > 0 && tune_flag("SCE_TOPK_SPARSE", heuristic);
+  }
   p->maps = new std::map<int, BatchMaps*>();
   carve(p, *desc, static_cast<uint8_t*>(b.workspace));
   *out_plan = p;

@@ -177,7 +177,8 @@ __global__ void __launch_bounds__(128) dict_rows_kernel(float* __restrict__ e, c
                                                         void* __restrict__ w_hi, void* __restrict__ w_lo,
                                                         void* __restrict__ w_x8, float* __restrict__ grad_out, int d,
                                                         int normalize, float floor, AdamHyper h,
-                                                        const uint32_t* __restrict__ health) {
+                                                        const uint32_t* __restrict__ health,
+                                                        float* __restrict__ w_f32 /*optional fp32 copy of w (top-k gather)*/) {
   __shared__ float red[8];
   if (MODE == MODE_ADAM && step_is_bad(health)) return;   // block-uniform: see kBadWord
   const long long row = blockIdx.x;
@@ -254,6 +255,7 @@ __global__ void __launch_bounds__(128) dict_rows_kernel(float* __restrict__ e, c
     if (c < d) {
       const float w[4] = {ev[i].x / s, ev[i].y / s, ev[i].z / s, ev[i].w / s};
       store_planes4<ARITH>(w, w_hi, w_lo, w_x8, (base + c) >> 2);
+      if (w_f32) *reinterpret_cast<float4*>(w_f32 + base + c) = make_float4(w[0], w[1], w[2], w[3]);
     }
   }
 }
@@ -430,9 +432,8 @@ __global__ void join_code_kernel(const void* __restrict__ hi, const void* __rest
 }
 
 // ------------------------------------------------------------------------------------------------
-// TopK selection (topk_encoder.py:19-27): per row keep the k largest signed scores, ReLU, and emit
-// the dense (hi, lo) code the decode / weight-gradient GEMMs read, plus the nnz / partial sums.
-// One 256-thread block per (model, row); 4-pass 8-bit radix select on order-preserving keys.
+// TopK selection helpers (topk_encoder.py:19-27; the kernels are in sce_topk.cuh): order-preserving keys, a
+// warp-aggregated histogram and a block-wide bin pick for the 8-bit radix select.
 // Ties at the k-th value are broken by lowest column index (torch.topk leaves this unspecified, Q8).
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t f2key(float f) {
@@ -479,205 +480,6 @@ __device__ __forceinline__ void pick_bin(const uint32_t* hist, uint32_t* sh_pref
 
 __device__ __forceinline__ float key2relu(uint32_t key) {  // relu(float behind an order-preserving key)
   return key > 0x80000000u ? __uint_as_float(key & 0x7FFFFFFFu) : 0.f;
-}
-
-// Rows are processed four elements per thread (n % 8 == 0 is guaranteed by the plan) with UNROLL independent
-// 16-byte loads in flight per thread: the first version (one 4-byte load per iteration) was latency-bound at
-// 1.1 TB/s (profiles: long-scoreboard stall 9.2 per issue).
-template <int ARITH>
-__global__ void __launch_bounds__(256) topk_select_kernel(const float* __restrict__ scores,
-                                                          const long long* __restrict__ sparsity,
-                                                          void* __restrict__ c_hi, void* __restrict__ c_lo,
-                                                          void* __restrict__ c_x8, ActMask act,
-                                                          float* __restrict__ part /*[M][B][2]*/, int B, int n,
-                                                          long long model_stride /*elements between models*/,
-                                                          int use_cand /*0: rows too long for a candidate list in smem*/) {
-  constexpr int UNROLL = 4;
-  extern __shared__ uint32_t smem_u[];
-  uint32_t* keys = smem_u;       // n keys of this row
-  uint32_t* cand = smem_u + n;   // candidates that share the leading digit of the k-th largest key
-  __shared__ uint32_t hist[256];
-  __shared__ uint32_t sh_prefix, sh_remaining, sh_ncand, sh_ties_before, sh_neq;
-  __shared__ uint32_t warp_cnt[8];
-  __shared__ float redf[16];
-  const int model = blockIdx.y;
-  const int row = blockIdx.x;
-  const long long base = (long long)model * model_stride + (long long)row * n;
-  const int n4 = n >> 2;
-  int k = (int)sparsity[model];
-  if (k > n) k = n;
-
-  // ---- load the row once: keys to shared memory, per-thread maximum in a register
-  if (threadIdx.x == 0) {
-    sh_ncand = 0;
-    sh_ties_before = 0;
-  }
-  uint32_t my_max = 0;
-  const float4* src4 = reinterpret_cast<const float4*>(scores + base);
-  for (int i0 = 0; i0 < n4; i0 += 256 * UNROLL) {
-    float4 v[UNROLL];
-#pragma unroll
-    for (int u = 0; u < UNROLL; ++u) {
-      const int i = i0 + u * 256 + threadIdx.x;
-      v[u] = i < n4 ? __ldg(src4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-#pragma unroll
-    for (int u = 0; u < UNROLL; ++u) {
-      const int i = i0 + u * 256 + threadIdx.x;
-      if (i < n4) {
-        const uint4 kk = make_uint4(f2key(v[u].x), f2key(v[u].y), f2key(v[u].z), f2key(v[u].w));
-        reinterpret_cast<uint4*>(keys)[i] = kk;
-        my_max = max(max(my_max, kk.x), max(kk.y, max(kk.z, kk.w)));
-      }
-    }
-  }
-  // 4-pass 8-bit radix select of the `want`-th largest of a set of keys; `each(f)` calls f(key) for the keys this
-  // thread contributes. Leaves the key in sh_prefix, the number of elements equal to it still to take in
-  // sh_remaining and (last pass) their total count in sh_neq.
-  auto radix_select = [&](uint32_t want, auto&& each) {
-    if (threadIdx.x == 0) {
-      sh_prefix = 0;
-      sh_remaining = want;
-    }
-    for (int pass = 0; pass < 4; ++pass) {
-      const int shift = 24 - 8 * pass;
-      hist[threadIdx.x] = 0;
-      __syncthreads();
-      const uint32_t prefix = sh_prefix;
-      const uint32_t pmask = pass == 0 ? 0u : (0xFFFFFFFFu << (shift + 8));
-      each([&](uint32_t kk, bool valid) { hist_add(hist, (kk >> shift) & 0xFF, valid && (kk & pmask) == prefix); });
-      __syncthreads();
-      pick_bin(hist, &sh_prefix, &sh_remaining, warp_cnt, shift, pass == 3 ? &sh_neq : nullptr);
-    }
-  };
-  // ---- a lower bound of the k-th largest key: the k-th largest of the 256 per-thread maxima (at least k elements
-  //      are >= it). Only elements >= that bound can be in the top k: typically one to a few k of them.
-  uint32_t bound = 0;                                     // k > 256: no pre-filter, every key is a candidate
-  if (k <= 256) {
-    radix_select((uint32_t)k, [&](auto&& f) { f(my_max, true); });
-    bound = sh_prefix;
-  }
-  __syncthreads();
-  if (use_cand) {
-    for (int i = threadIdx.x; i < n4; i += 256) {
-      const uint4 kk = reinterpret_cast<const uint4*>(keys)[i];
-      if (kk.x >= bound) cand[atomicAdd(&sh_ncand, 1u)] = kk.x;
-      if (kk.y >= bound) cand[atomicAdd(&sh_ncand, 1u)] = kk.y;
-      if (kk.z >= bound) cand[atomicAdd(&sh_ncand, 1u)] = kk.z;
-      if (kk.w >= bound) cand[atomicAdd(&sh_ncand, 1u)] = kk.w;
-    }
-    __syncthreads();
-    const int ncand = (int)sh_ncand;
-    // ---- exact selection among the candidates (order of `cand` is irrelevant)
-    radix_select((uint32_t)k, [&](auto&& f) {
-      for (int i0 = 0; i0 < ncand; i0 += 256) {
-        const int i = i0 + threadIdx.x;
-        f(i < ncand ? cand[i] : 0u, i < ncand);
-      }
-    });
-  } else {
-    // very long rows: no room for a candidate list, select over the keys that pass the bound in place
-    radix_select((uint32_t)k, [&](auto&& f) {
-      for (int i0 = 0; i0 < n; i0 += 256) {
-        const int i = i0 + threadIdx.x;
-        const uint32_t kk = i < n ? keys[i] : 0u;
-        f(kk, i < n && kk >= bound);
-      }
-    });
-  }
-  const uint32_t kth = sh_prefix;          // exact key of the k-th largest
-  const uint32_t take_ties = sh_remaining; // number of elements == kth to keep
-  const bool all_ties_kept = sh_neq == take_ties;
-  float l1 = 0.f, cnt = 0.f;
-  // Called by every thread of the block in lockstep (`valid` false past the end of the row): besides the code planes it
-  // assembles the activity-mask word of each 32-column chunk from the eight threads that own it (relu semantics: the
-  // z == 0 plane stays empty).
-  auto emit = [&](int i, bool valid, float c0, float c1, float c2, float c3) {
-    uint32_t bits = 0;
-    if (valid) {
-      const float cv4[4] = {c0, c1, c2, c3};
-      store_planes4<ARITH>(cv4, c_hi, c_lo, c_x8, (base >> 2) + i);
-      l1 += c0 + c1 + c2 + c3;
-      bits = (c0 > 0.f ? 8u : 0u) | (c1 > 0.f ? 4u : 0u) | (c2 > 0.f ? 2u : 0u) | (c3 > 0.f ? 1u : 0u);
-      cnt += float(__popc(bits));
-    }
-    uint32_t w = bits << (28 - 4 * (i & 7));   // columns 4 (i % 8) .. + 3 of chunk i / 8; bit 31 - j is column j
-    w |= __shfl_xor_sync(0xffffffffu, w, 1);
-    w |= __shfl_xor_sync(0xffffffffu, w, 2);
-    w |= __shfl_xor_sync(0xffffffffu, w, 4);
-    if (valid && (i & 7) == 0) {
-      act.pos[act.at(model, i >> 3, row)] = w;
-    }
-  };
-  if (all_ties_kept) {
-    // the common case (no exact tie straddling the cut): keep = key >= kth; values come back out of the keys
-    for (int i0 = 0; i0 < n4; i0 += 256) {
-      const int i = i0 + threadIdx.x;
-      const bool valid = i < n4;
-      const uint4 kk = valid ? reinterpret_cast<const uint4*>(keys)[i] : make_uint4(0, 0, 0, 0);
-      emit(i, valid, kk.x >= kth ? key2relu(kk.x) : 0.f, kk.y >= kth ? key2relu(kk.y) : 0.f,
-           kk.z >= kth ? key2relu(kk.z) : 0.f, kk.w >= kth ? key2relu(kk.w) : 0.f);
-    }
-  } else {
-    // exact ties at the cut: keep the first `take_ties` of them in index order (ordered block scan)
-    for (int i0 = 0; i0 < n4; i0 += 256) {
-      const int i = i0 + threadIdx.x;
-      uint4 kk = make_uint4(0, 0, 0, 0);
-      if (i < n4) kk = reinterpret_cast<const uint4*>(keys)[i];
-      const uint32_t kv[4] = {kk.x, kk.y, kk.z, kk.w};
-      int mine = 0;
-#pragma unroll
-      for (int u = 0; u < 4; ++u) mine += (i < n4 && kv[u] == kth) ? 1 : 0;
-      // exclusive prefix of tie counts over the block, in element order (thread t owns elements 4i..4i+3)
-      int incl = mine;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int v = __shfl_up_sync(0xffffffffu, incl, o);
-        if ((threadIdx.x & 31) >= o) incl += v;
-      }
-      if ((threadIdx.x & 31) == 31) warp_cnt[threadIdx.x >> 5] = (uint32_t)incl;
-      __syncthreads();
-      uint32_t before = sh_ties_before + (uint32_t)(incl - mine);
-      for (int w = 0; w < (threadIdx.x >> 5); ++w) before += warp_cnt[w];
-      {
-        float cv[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const bool tie = kv[u] == kth;
-          const bool keep = kv[u] > kth || (tie && before < take_ties);
-          if (tie) ++before;
-          cv[u] = (i < n4 && keep) ? key2relu(kv[u]) : 0.f;
-        }
-        emit(i, i < n4, cv[0], cv[1], cv[2], cv[3]);
-      }
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        uint32_t t = 0;
-        for (int w = 0; w < 8; ++w) t += warp_cnt[w];
-        sh_ties_before += t;
-      }
-      __syncthreads();
-    }
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    l1 += __shfl_xor_sync(0xffffffffu, l1, o);
-    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-  }
-  if ((threadIdx.x & 31) == 0) {
-    redf[threadIdx.x >> 5] = l1;
-    redf[8 + (threadIdx.x >> 5)] = cnt;
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    float a = 0, b = 0;
-    for (int w = 0; w < 8; ++w) {
-      a += redf[w];
-      b += redf[8 + w];
-    }
-    part[((long long)model * B + row) * 2] = a;
-    part[((long long)model * B + row) * 2 + 1] = b;
-  }
 }
 
 }  // namespace sce

@@ -254,7 +254,8 @@ class FunctionalEnsemble:
             adam_count_mode=_lib.SCE_ADAM_FROZEN_T1 if self.adam_count_mode == "frozen_t1" else _lib.SCE_ADAM_STANDARD,
             fwd_passes=self.fwd_passes, bwd_passes=self.bwd_passes,
             norm_floor=0.0 if self._variant == "topk" else 1e-8,
-            arith=_lib.ARITH_CODE[getattr(self, "_arith_fallback", None) or getattr(self, "arith", "auto")])
+            arith=_lib.ARITH_CODE[getattr(self, "_arith_fallback", None) or getattr(self, "arith", "auto")],
+            topk_k_max=int(self.buffers["sparsity"].max()) if self._variant == "topk" else 0)
         nbytes = lib.sce_workspace_bytes(C.byref(desc))
         if nbytes == 0:
             _lib.check(-1, "sce_workspace_bytes")
