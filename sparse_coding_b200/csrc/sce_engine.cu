@@ -661,10 +661,8 @@ static int run_pipeline_t(sce_plan* p, const float* x, int B, float* x_hat, bool
                                                  one, dd, d.fwd_passes, B, n, sp, st, x_is_a);
     if (rc) return rc;
     ++launches;
-    if ((size_t)n * 4 > 200 * 1024) return fail(SCE_ERR_INVALID, "top-k: n = %d exceeds the shared-memory row buffer", n);
     static bool cfg[64] = {};
     if (p->device < 0 || p->device >= 64 || !cfg[p->device]) {
-      CUDA_TRY(cudaFuncSetAttribute(topk_select2_kernel<AR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       CUDA_TRY(cudaFuncSetAttribute(topk_sparse_kernel<AR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
       if (p->device >= 0 && p->device < 64) cfg[p->device] = true;
     }
@@ -674,8 +672,9 @@ static int run_pipeline_t(sce_plan* p, const float* x, int B, float* x_hat, bool
     tk.kmax = p->tk_kmax;
     tk.batch_max = d.batch_max;
     // one block per (row, model); scores / codes of model m start at m * batch_max * n
-    topk_select2_kernel<AR><<<dim3(B, M), 256, (size_t)n * 4, st>>>(p->scores, p->b.sparsity, p->c_hi, p->c_lo, p->c_x8, act,
-                                                                     tk, p->part_enc, B, n, Bm * n);
+    topk_select2_kernel<AR><<<dim3(B, M), 256, 0, st>>>(
+        p->scores, p->b.sparsity, p->c_hi, p->c_lo, p->c_x8, p->topk_sparse ? (void*)p->dz_hi : nullptr, p->dz_lo, p->dz_x8,
+        act, tk, p->part_enc, B, n, Bm * n);
     ++launches;
     CUDA_TRY(cudaGetLastError());
     n_enc_parts = B;
@@ -736,7 +735,7 @@ static int run_pipeline_t(sce_plan* p, const float* x, int B, float* x_hat, bool
   if (backward) {
     if (sparse) {
       // ---- code gradient planes: zero the rows, scatter the k entries
-      topk_dz_scatter_kernel<AR><<<dim3(B, M), 256, 0, st>>>(tk, p->tk_dots, p->tk_slices, p->dz_hi, p->dz_lo, p->dz_x8, n);
+      topk_dz_scatter_kernel<AR><<<dim3(B, M), 64, 0, st>>>(tk, p->tk_dots, p->tk_slices, p->dz_hi, p->dz_lo, p->dz_x8, n);
       ++launches;
       CUDA_TRY(cudaGetLastError());
     } else {
@@ -922,6 +921,18 @@ int sce_prepare(sce_plan* p, void* stream) {
   CUDA_TRY(cudaMemsetAsync(p->res_flags, 0, kFlagWords * sizeof(uint32_t), st));   // residual flag, input range monitor, health
   const sce_desc& d = p->d;
   const long long rows = (long long)d.n_models * d.n;
+  if (d.variant == SCE_TOPK && p->tk_kmax) {
+    // the top-k selection keeps the code planes (and, in k-sparse plans, the code-gradient planes) all-zero except for
+    // the entries its lists record: start them zeroed, with empty lists
+    const size_t el = (size_t)d.n_models * d.batch_max * d.n;
+    const bool f8 = p->arith == kArithF16F8;
+    CUDA_TRY(cudaMemsetAsync(p->c_hi, 0, el * 2, st));
+    CUDA_TRY(cudaMemsetAsync(p->c_lo, 0, el * (f8 ? 1 : 2), st));
+    if (f8) CUDA_TRY(cudaMemsetAsync(p->c_x8, 0, el, st));
+    CUDA_TRY(cudaMemsetAsync(p->dz_hi, 0, el * 4, st));   // (the code-gradient planes are one contiguous block, 4 B / element)
+    CUDA_TRY(cudaMemsetAsync(p->act_pos, 0, (size_t)d.n_models * ((d.n + 31) / 32) * d.batch_max * sizeof(uint32_t), st));
+    CUDA_TRY(cudaMemsetAsync(p->tk_cnt, 0, (size_t)d.n_models * d.batch_max * sizeof(int), st));
+  }
   AdamHyper h = hyper_for(p, 1);
   int rc;
   if (d.variant == SCE_UNTIED) {

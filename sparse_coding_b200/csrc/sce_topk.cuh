@@ -36,6 +36,18 @@ __device__ __forceinline__ void store_plane1(float v, void* hi, void* lo, void* 
   }
 }
 
+// one element of every plane back to zero
+template <int ARITH>
+__device__ __forceinline__ void store_plane_zero(void* hi, void* lo, void* x8, long long i) {
+  reinterpret_cast<uint16_t*>(hi)[i] = 0;
+  if constexpr (ARITH == kArithF16F8) {
+    reinterpret_cast<uint8_t*>(lo)[i] = 0;
+    reinterpret_cast<uint8_t*>(x8)[i] = 0;
+  } else {
+    reinterpret_cast<uint16_t*>(lo)[i] = 0;
+  }
+}
+
 // zero `count` consecutive elements (count % 8 == 0, offset % 8 == 0) of every plane with 16-byte stores, block-wide
 template <int ARITH>
 __device__ __forceinline__ void zero_planes_row(void* hi, void* lo, void* x8, long long off, int count) {
@@ -66,15 +78,21 @@ struct TopkLists {
 };
 
 // ------------------------------------------------------------------------------------------------
-// selection. One 256-thread block per (row, model); the row's order-preserving keys live in shared memory.
-//   1. load the row once (16-byte loads), keys -> smem, per-thread maximum; zero the row of the code planes / mask
+// selection. One 256-thread block per (row, model). The row is read twice with 16-byte loads — the second time out
+// of L2 — instead of being parked in shared memory: 9 KB of shared memory per block keep eight blocks on an SM
+// (with the keys in shared memory, 24-49 KB per row, the kernel sat at 37 % warp occupancy and 44 % of the DRAM rate).
+//   1. first pass over the row: per-thread maximum of the order-preserving keys. Meanwhile the row of the code planes
+//      and of the activity mask is returned to all-zero: with lists (the plan knows k) by clearing the entries the
+//      PREVIOUS call scattered — the planes start zeroed (sce_prepare) and every write to them is recorded in the
+//      row's list, so k clears replace rewriting n zeros (half of this kernel's DRAM traffic) —, else by zeroing it.
+//      In k-sparse plans the code-gradient planes are kept the same way (topk_dz_scatter_kernel only scatters).
 //   2. a lower bound of the k-th largest key: every warp sorts its 32 thread maxima, takes its ceil(k/8)-th largest;
 //      the minimum over the 8 warps has at least k elements at or above it
-//   3. the keys >= bound (typically 1-3 k of them) are compacted into a candidate list
+//   3. second pass: the keys >= bound (typically 1-3 k of them) are compacted into a candidate list
 //   4. exact rank of every candidate by counting (keys made unique by the column: ties go to the lowest column):
 //      rank < k <=> selected, and rank is its slot in the list               — no sort, no radix passes
-//      (more candidates than the list holds — k > 256, many equal scores — : 4-pass radix select over the keys in
-//      place and an ordered compaction, as the first version of this kernel did for every row)
+//      (more candidates than the list holds — k > 256, many equal scores — : 4-pass radix select re-reading the row
+//      each pass, then an ordered compaction, as the first version of this kernel did for every row from shared memory)
 //   5. scatter the k entries into the zeroed planes, activity-mask bits, (column, value) list, per-row partials
 // ------------------------------------------------------------------------------------------------
 constexpr int kTopkCand = 1024;
@@ -83,12 +101,12 @@ template <int ARITH>
 __global__ void __launch_bounds__(256) topk_select2_kernel(const float* __restrict__ scores,
                                                            const long long* __restrict__ sparsity,
                                                            void* __restrict__ c_hi, void* __restrict__ c_lo,
-                                                           void* __restrict__ c_x8, ActMask act, TopkLists lists,
+                                                           void* __restrict__ c_x8, void* __restrict__ dz_hi,
+                                                           void* __restrict__ dz_lo, void* __restrict__ dz_x8,
+                                                           ActMask act, TopkLists lists,
                                                            float* __restrict__ part /*[M][B][2]*/, int B, int n,
                                                            long long model_stride /*elements between models*/) {
   constexpr int UNROLL = 4;
-  extern __shared__ uint32_t smem_u[];
-  uint32_t* keys = smem_u;   // n keys of this row
   __shared__ uint32_t cand_key[kTopkCand];
   __shared__ int cand_col[kTopkCand];
   __shared__ uint32_t hist[256];
@@ -107,9 +125,13 @@ __global__ void __launch_bounds__(256) topk_select2_kernel(const float* __restri
     sh_kept = 0;
     sh_ties = 0;
   }
-  // ---- 1. the row: keys to shared memory, per-thread maximum; meanwhile clear this row of the outputs
+  // ---- 1. first pass over the row: per-thread maximum; meanwhile clear this row of the outputs
   uint32_t my_max = 0;
   const float4* src4 = reinterpret_cast<const float4*>(scores + base);
+  auto key4 = [&](int i) {   // keys of elements 4i .. 4i+3 (i < n4)
+    const float4 v = __ldg(src4 + i);
+    return make_uint4(f2key(v.x), f2key(v.y), f2key(v.z), f2key(v.w));
+  };
   for (int i0 = 0; i0 < n4; i0 += 256 * UNROLL) {
     float4 v[UNROLL];
 #pragma unroll
@@ -122,13 +144,24 @@ __global__ void __launch_bounds__(256) topk_select2_kernel(const float* __restri
       const int i = i0 + u * 256 + threadIdx.x;
       if (i < n4) {
         const uint4 kk = make_uint4(f2key(v[u].x), f2key(v[u].y), f2key(v[u].z), f2key(v[u].w));
-        reinterpret_cast<uint4*>(keys)[i] = kk;
         my_max = max(max(my_max, kk.x), max(kk.y, max(kk.z, kk.w)));
       }
     }
   }
-  zero_planes_row<ARITH>(c_hi, c_lo, c_x8, base, n);
-  for (int ch = threadIdx.x; ch < act.n_chunks; ch += 256) act.pos[act.at(model, ch, row)] = 0u;
+  const long long lbase = lists.kmax ? ((long long)model * lists.batch_max + row) * lists.kmax : 0;
+  if (lists.kmax) {
+    // clear what the previous call left in this row (dz_* != nullptr: k-sparse plan, same entries in the code gradient)
+    const int old = lists.cnt[(long long)model * lists.batch_max + row];
+    for (int j = threadIdx.x; j < old; j += 256) {
+      const int col = lists.col[lbase + j];
+      store_plane_zero<ARITH>(c_hi, c_lo, c_x8, base + col);
+      if (dz_hi) store_plane_zero<ARITH>(dz_hi, dz_lo, dz_x8, base + col);
+      act.pos[act.at(model, col >> 5, row)] = 0u;   // (several old entries may share the word: they all write 0)
+    }
+  } else {
+    zero_planes_row<ARITH>(c_hi, c_lo, c_x8, base, n);
+    for (int ch = threadIdx.x; ch < act.n_chunks; ch += 256) act.pos[act.at(model, ch, row)] = 0u;
+  }
   // ---- 2. lower bound of the k-th largest key
   uint32_t bound = 0;   // k > 256: every key is a candidate (the radix path below takes over)
   if (k <= 256) {
@@ -151,24 +184,33 @@ __global__ void __launch_bounds__(256) topk_select2_kernel(const float* __restri
 #pragma unroll
     for (int w = 1; w < 8; ++w) bound = min(bound, warp_bound[w]);
   }
-  // ---- 3. candidates
-  for (int i = threadIdx.x; i < n4; i += 256) {
-    const uint4 kk = reinterpret_cast<const uint4*>(keys)[i];
-    const uint32_t kv[4] = {kk.x, kk.y, kk.z, kk.w};
+  // ---- 3. candidates (second pass over the row, L2-resident)
+  for (int i0 = 0; i0 < n4; i0 += 256 * UNROLL) {
+    float4 v[UNROLL];
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
-      if (kv[u] >= bound) {
-        const uint32_t slot = atomicAdd(&sh_ncand, 1u);
-        if (slot < kTopkCand) {
-          cand_key[slot] = kv[u];
-          cand_col[slot] = 4 * i + u;
+    for (int u = 0; u < UNROLL; ++u) {
+      const int i = i0 + u * 256 + threadIdx.x;
+      v[u] = i < n4 ? __ldg(src4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const int i = i0 + u * 256 + threadIdx.x;
+      if (i >= n4) continue;
+      const uint32_t kv[4] = {f2key(v[u].x), f2key(v[u].y), f2key(v[u].z), f2key(v[u].w)};
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (kv[e] >= bound) {
+          const uint32_t slot = atomicAdd(&sh_ncand, 1u);
+          if (slot < kTopkCand) {
+            cand_key[slot] = kv[e];
+            cand_col[slot] = 4 * i + e;
+          }
         }
-      }
+    }
   }
   __syncthreads();
   const int ncand = (int)sh_ncand;
   float l1 = 0.f, cnt = 0.f;
-  const long long lbase = lists.kmax ? ((long long)model * lists.batch_max + row) * lists.kmax : 0;
   auto emit = [&](int slot, int col, uint32_t key) {   // entry `slot` of the selection: column `col`
     const float v = key2relu(key);
     store_plane1<ARITH>(v, c_hi, c_lo, c_x8, base + col);
@@ -208,7 +250,7 @@ __global__ void __launch_bounds__(256) topk_select2_kernel(const float* __restri
       const uint32_t pmask = pass == 0 ? 0u : (0xFFFFFFFFu << (shift + 8));
       for (int i0 = 0; i0 < n; i0 += 256) {
         const int i = i0 + threadIdx.x;
-        const uint32_t kk = i < n ? keys[i] : 0u;
+        const uint32_t kk = i < n ? f2key(__ldg(scores + base + i)) : 0u;
         hist_add(hist, (kk >> shift) & 0xFF, i < n && kk >= bound && (kk & pmask) == prefix);
       }
       __syncthreads();
@@ -219,7 +261,7 @@ __global__ void __launch_bounds__(256) topk_select2_kernel(const float* __restri
     for (int i0 = 0; i0 < n4; i0 += 256) {
       const int i = i0 + threadIdx.x;
       uint4 kk = make_uint4(0, 0, 0, 0);
-      if (i < n4) kk = reinterpret_cast<const uint4*>(keys)[i];
+      if (i < n4) kk = key4(i);
       const uint32_t kv[4] = {kk.x, kk.y, kk.z, kk.w};
       int ties = 0, greater = 0;
 #pragma unroll
@@ -425,18 +467,16 @@ __global__ void __launch_bounds__(256) topk_sparse_kernel(TopkLists lists, const
   }
 }
 
-// dense operand planes of the code gradient for the weight-gradient GEMM: zero the row, scatter the k entries
+// dense operand planes of the code gradient for the weight-gradient GEMM: scatter the k entries into the zeroed row
 //   dz[row][col_j] = [c_j > 0] * sum_slices dots[row][j][slice]              (relu: no gradient at exactly 0)
 template <int ARITH>
-__global__ void __launch_bounds__(256) topk_dz_scatter_kernel(TopkLists lists, const float* __restrict__ dots, int slices,
+__global__ void __launch_bounds__(64) topk_dz_scatter_kernel(TopkLists lists, const float* __restrict__ dots, int slices,
                                                               void* __restrict__ dz_hi, void* __restrict__ dz_lo,
                                                               void* __restrict__ dz_x8, int n) {
   const int row = blockIdx.x, model = blockIdx.y;
   const long long lrow = (long long)model * lists.batch_max + row;
-  zero_planes_row<ARITH>(dz_hi, dz_lo, dz_x8, lrow * n, n);
-  __syncthreads();
-  const int cnt = lists.cnt[lrow];
-  for (int j = threadIdx.x; j < cnt; j += 256) {
+  const int cnt = lists.cnt[lrow];   // (the row is all-zero: the selection cleared the previous step's entries)
+  for (int j = threadIdx.x; j < cnt; j += 64) {
     const long long e = lrow * lists.kmax + j;
     if (lists.val[e] > 0.f) {
       float v = 0.f;
