@@ -54,6 +54,7 @@ struct GemmMaps {  // tensor maps of one GEMM for one batch size (x8: third plan
 struct BatchMaps {
   GemmMaps encode, decode, dcode, dw_enc, dw_dec;
   CUtensorMap st_c_hi, st_c_lo, st_c_x8, st_dz_hi, st_dz_lo, st_dz_x8;  // epilogue TMA-store maps
+  CUtensorMap st_scores;                                                // top-k: fp32 scores
   cudaGraphExec_t graph;       // captured step for this batch size (launch-bound shapes), or nullptr
   int graph_launches, eager_steps;
 };
@@ -407,6 +408,7 @@ static int build_maps(sce_plan* p, int B, BatchMaps** out) {
     ok &= make_tmap_bf16_store32(&m->st_c_lo, p->c_lo, M, (uint64_t)B, n, Bm * n);
     ok &= make_tmap_bf16_store32(&m->st_dz_lo, p->dz_lo, M, (uint64_t)B, n, Bm * n);
   }
+  if (d.variant == SCE_TOPK) ok &= make_tmap_f32_store32(&m->st_scores, p->scores, M, (uint64_t)B, n, Bm * n);
   if (!ok) {
     delete m;
     return fail(SCE_ERR_CUDA, "cuTensorMapEncodeTiled failed (B=%d, M=%d, n=%d, d=%d)", B, d.n_models, d.n, d.d);
@@ -652,12 +654,9 @@ static int run_pipeline_t(sce_plan* p, const float* x, int B, float* x_hat, bool
     n_enc_parts = tiles_mB * 8 * ep.tiles_n;
   } else {
     // scores -> fp32, then per-row selection (code planes, activity mask, k-sparse lists)
-    EpiStoreF32::Params sp;
-    sp.out = p->scores;
-    sp.model_stride = Bm * n;
-    sp.ld = n;
-    sp.scale = 1.f;
-    rc = launch_k<EpiStoreF32, false, false, AR>(n > 128, p->bk_encode, pair_ok(p->pair_encode, B, n), p, maps->encode, 1, xb,
+    EpiScoresTma::Params sp;
+    sp.out = maps->st_scores;
+    rc = launch_k<EpiScoresTma, false, false, AR>(n > 128, p->bk_encode, pair_ok(p->pair_encode, B, n), p, maps->encode, 1, xb,
                                                  one, dd, d.fwd_passes, B, n, sp, st, x_is_a);
     if (rc) return rc;
     ++launches;

@@ -405,6 +405,46 @@ struct EpiDcodeT {
   }
 };
 
+// ------------------------------------------------------------------------------------------------
+// scores of the top-k variant: acc -> fp32 [M][B][n] through the same staging + bulk-store path as the code planes
+// (each epilogue warp owns a 4 KB tile of 32 rows x 128 B, 128-byte swizzle: a thread writes its row with eight
+// conflict-free 16-byte stores, one lane hands the tile to the TMA engine, which writes full lines and clips the
+// ragged edges). The plain per-thread stores of EpiStoreF32 touch 32 different lines per instruction — fine for
+// the small weight-gradient output, but the scores GEMM (K = d only, 4 B per element out) was bound by them.
+// ------------------------------------------------------------------------------------------------
+struct EpiScoresTma {
+  static constexpr int kCols = 32;
+  static constexpr int kWarpStageBytes = 4096;
+  struct Params {
+    CUtensorMap out;   // [M][B][n] fp32, box 32 x 32
+  };
+  const Params& P;
+  const TileCoord& T;
+  int m_total, n_total;
+  uint8_t* stage;
+  __device__ EpiScoresTma(const Params& p, const TileCoord& t, int m, int n, uint8_t* st)
+      : P(p), T(t), m_total(m), n_total(n), stage(st) {}
+  __device__ __forceinline__ void chunk(int c, const uint32_t (&r)[32]) {
+    const int col = T.col0 + c;
+    if (col >= n_total) return;   // warp-uniform
+    if (T.lane == 0) tma_store_wait_read();
+    __syncwarp();
+    const int sw = T.lane & 7;
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+      *reinterpret_cast<uint4*>(stage + T.lane * 128 + ((q ^ sw) << 4)) = make_uint4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (T.lane == 0) {
+      tma_store_3d(&P.out, stage, col, T.m_blk * kBM + T.warp_q * 32, T.model);
+      tma_store_commit();
+    }
+  }
+  __device__ __forceinline__ void finish() {
+    if (T.lane == 0) tma_store_wait_read();
+  }
+};
+
 using EpiEncode = EpiEncodeT<kArithBf16x3>;
 using EpiDecode = EpiDecodeT<kArithBf16x3>;
 using EpiDcode = EpiDcodeT<kArithBf16x3>;

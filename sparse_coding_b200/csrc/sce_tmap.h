@@ -76,4 +76,20 @@ inline bool make_tmap_u8_box(CUtensorMap* map, const void* base, uint64_t models
   return r == CUDA_SUCCESS;
 }
 
+// An fp32 tensor [models][rows][cols] written in boxes of [1][32 rows][32 cols] (128-byte rows, 128-byte swizzle):
+// the epilogue store map of the top-k scores.
+inline bool make_tmap_f32_store32(CUtensorMap* map, const void* base, uint64_t models, uint64_t rows, uint64_t cols,
+                                  uint64_t model_pitch_elems) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[3] = {cols, rows, models};
+  cuuint64_t strides[2] = {cols * 4, model_pitch_elems * 4};
+  cuuint32_t box[3] = {32, 32, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
 }  // namespace sce
