@@ -479,6 +479,7 @@ def main():
     ap.add_argument("--no-alt", action="store_true", help="skip the informational single-pass-backward run")
     ap.add_argument("--no-stock", action="store_true", help="skip the stock-PyTorch-on-this-GPU comparator")
     ap.add_argument("--no-stream", action="store_true", help="skip the config-4 chunk-streaming extras")
+    ap.add_argument("--stream-timeout", type=float, default=240.0, help="watchdog of the config-4 extras, seconds")
     ap.add_argument("--stream-chunks", type=int, default=3)
     ap.add_argument("--stream-rows", type=int, default=1 << 21, help="rows per streamed chunk (reference: 2^21 at d=512)")
     ap.add_argument("--feed", default="per_rank", choices=["per_rank", "broadcast", "both"],
@@ -643,24 +644,7 @@ def main():
     ms, ms_e2e, ms_serial = float(t[0]), float(t[1]), float(t[2])
     clocks = sampler.stop(windows) if rank == 0 else None
 
-    # ---------------- config 4's data path (all ranks take part)
-    stream = None
-    if (args.workload == "cfg2" and not args.no_stream) or stream_only:
-        for e in enss:
-            e._destroy_plan()
-        del pool
-        torch.cuda.empty_cache()
-        feeds = ["per_rank", "broadcast"] if (args.feed == "both" and world > 1) else \
-            [args.feed if (world > 1 or args.feed == "per_rank") and args.feed != "both" else "per_rank"]
-        stream = {}
-        for feed in feeds:
-            try:
-                stream[feed] = run_stream(S, dist, rank, world, dev, M, d, n, B, args.stream_chunks, args.stream_rows, feed,
-                                          ms / K)
-            except Exception as exc:                                      # extras must never cost the headline line
-                stream[feed] = {"failed": f"{type(exc).__name__}: {exc}"}
-        pool = [x.to(dev) for x in host[:4]]
-
+    line = None
     if rank == 0:
         pk = peaks()
         arith = arith_resolved
@@ -760,8 +744,6 @@ def main():
                                              "forward, losses and x̂ unchanged; FVU/L0 parity of this mode at this size: "
                                              "tests/test_scale_parity_gpu.py::test_training_quality_at_config2_scale",
                                      "value": B * K / (ms_alt * 1e-3), "ms_per_step": ms_alt / K}
-        if stream is not None:
-            line["cfg4_stream"] = stream[next(iter(stream))] if len(stream) == 1 else stream
         if world == 1 and not args.no_stock and args.workload in ("cfg2", "cfg1"):
             try:
                 line["stock_torch_gpu"] = stock_torch_gpu(M, d, n, B, dev, pool)
@@ -773,6 +755,40 @@ def main():
             rate, sample, cores, dt, Bs = cpu_reference_rate(M, d, n, B, budget_s=45.0, steps=1, warmup=0)
             line["cpu_baseline"] = {"value": rate, "unit": "activations/s", "cores": cores, "kind": "port",
                                     "sample": sample, "same_config": bool(Bs == B)}
+
+    # ---------------- config 4's data path (all ranks take part). It runs AFTER the line is complete and under a
+    # watchdog: if a rank fails or a collective hangs in here, rank 0 still prints the line (without these extras).
+    stream = None
+    if (args.workload == "cfg2" and not args.no_stream) or stream_only:
+        import threading
+
+        def bail():
+            if rank == 0 and line is not None:
+                line["cfg4_stream"] = {"failed": f"no result within {args.stream_timeout} s (watchdog)"}
+                out.emit(line)
+            os._exit(0)
+
+        timer = threading.Timer(args.stream_timeout, bail)
+        timer.daemon = True
+        timer.start()
+        for e in enss:
+            e._destroy_plan()
+        del pool
+        torch.cuda.empty_cache()
+        feeds = ["per_rank", "broadcast"] if (args.feed == "both" and world > 1) else \
+            [args.feed if (world > 1 or args.feed == "per_rank") and args.feed != "both" else "per_rank"]
+        stream = {}
+        for feed in feeds:
+            try:
+                stream[feed] = run_stream(S, dist, rank, world, dev, M, d, n, B, args.stream_chunks, args.stream_rows, feed,
+                                          ms / K)
+            except Exception as exc:                                      # extras must never cost the headline line
+                stream[feed] = {"failed": f"{type(exc).__name__}: {exc}"}
+        timer.cancel()
+
+    if rank == 0:
+        if stream is not None:
+            line["cfg4_stream"] = stream[next(iter(stream))] if len(stream) == 1 else stream
         if stream_only and stream:
             first = stream[next(iter(stream))]
             if "value" in first:                       # this workload's own metric: the streamed rate
@@ -783,8 +799,6 @@ def main():
                                "how": "the streamed run IS end to end: chunk bytes cross PCIe once (fp16), batches are "
                                       "gathered on the device"}
         out.emit(line)
-    elif (args.workload == "cfg2" and not args.no_stream) or stream_only:
-        pass
     if world > 1:
         dist.destroy_process_group()
 
