@@ -220,3 +220,20 @@ def test_staged_upload_is_bit_exact():
     assert torch.equal(out.cpu(), t)
     small = torch.randn(10, 8)
     assert torch.equal(_to_device_staged(small, torch.device("cuda")).cpu(), small)
+
+
+def test_chunk_streamer_ring_of_pinned_pieces(tmp_path):
+    """ChunkStreamer moves a chunk through a small ring of pinned pieces; with pieces much smaller than the chunk
+    (ring reused many times, ragged last piece) the device copy is bit-exact and chunks arrive in order."""
+    from sparse_coding_b200.train_loop import ChunkStreamer
+    gen = torch.Generator().manual_seed(0)
+    chunks = [torch.randn(1000 + 37 * i, 96, generator=gen).half() for i in range(3)]
+    for i, c in enumerate(chunks):
+        torch.save(c, tmp_path / f"{i}.pt")
+    st = ChunkStreamer(str(tmp_path), [2, 0, 1, 0], "cuda")
+    st.PIECE_BYTES = 10_000                                   # 20+ pieces per chunk through a ring of 4
+    seen = []
+    for idx, dev in st:
+        assert torch.equal(dev.cpu(), chunks[idx])
+        seen.append(idx)
+    assert seen == [2, 0, 1, 0] and len(st.stage_seconds) == 4

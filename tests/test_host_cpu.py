@@ -250,3 +250,22 @@ def test_from_state_continues_the_step_count_of_a_dead_worker():
     assert S.FunctionalEnsemble.from_state(sd)._steps == 12
     frozen = S.FunctionalEnsemble(models, S.FunctionalTiedSAE, S.adam, {"lr": 1e-3}, device="cpu")
     assert S.FunctionalEnsemble.from_state(frozen.state_dict())._steps == 0
+
+
+def test_permutation_cache_changes_nothing():
+    """_batch_index_lists with a cache returns exactly the batches it returns without one (the reference re-seeds the
+    global RNG per chunk, so equal-length chunks draw the same permutation: SURVEY Q7), also after the cache was filled
+    under another seed or chunk length."""
+    from sparse_coding_b200.train_loop import _batch_index_lists
+    mk = lambda n: torch.utils.data.BatchSampler(torch.utils.data.RandomSampler(range(n)), batch_size=64, drop_last=False)
+    cache = {}
+    for seed, n in ((0, 1000), (0, 1000), (5, 1000), (0, 777), (0, 1000)):
+        torch.manual_seed(seed)
+        plain = [b.clone() for b in _batch_index_lists(mk(n))]
+        torch.manual_seed(seed)
+        cached = [b.clone() for b in _batch_index_lists(mk(n), None, cache)]
+        torch.manual_seed(seed)
+        ref = [torch.tensor(ix) for ix in mk(n)]                      # what the reference's loop iterates over
+        assert len(plain) == len(cached) == len(ref) == -(-n // 64)
+        assert all(torch.equal(a, b) and torch.equal(a, c) for a, b, c in zip(plain, cached, ref))
+    assert 1 <= len(cache) <= 4
