@@ -56,3 +56,45 @@ def tied_step_emulated(mm, x, W, bias, alpha, pin_active=None):
     dz = ((mm(r, W.T.contiguous()).float() + alpha * d / 2) * active).float()
     dW = (mm(dz.T.contiguous(), x) + mm(c.T.contiguous(), r)) * (2.0 / (B * d))
     return z, x_hat, dW
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Candidate (NOT implemented on the device): cross terms on block-scaled 4-bit planes
+# (tcgen05 kind::mxf4: E2M1 elements, one E8M0 scale per 32 elements along K, K = 64 per instruction at four times the
+# kind::f16 rate): 1 + 2 * 1/4 = 1.5 pass-equivalents and 2 + 0.5 + 0.5 (+ scales) ~= 3.06 bytes per operand element.
+# ----------------------------------------------------------------------------------------------------------------
+_E2M1 = torch.tensor([0.0, 0.5, 1.0, 1.5, 2.0, 3.0, 4.0, 6.0])
+
+
+def mxfp4(t: torch.Tensor, block: int = 32, saturate: bool = True) -> torch.Tensor:
+    """Values of `t` after MXFP4 quantisation along the LAST dim (blocks of `block`; zero-padded): shared power-of-two
+    scale 2^(floor(log2(amax)) - 2) as in the OCP MX spec (elements in (6, 8) * scale then saturate to 6), or with
+    ``saturate=False`` the next scale up (nothing saturates, one bit less for the rest of the block)."""
+    t = t.double()
+    k = t.shape[-1]
+    pad = (-k) % block
+    if pad:
+        t = torch.nn.functional.pad(t, (0, pad))
+    b = t.reshape(*t.shape[:-1], -1, block)
+    amax = b.abs().amax(dim=-1, keepdim=True).clamp(min=1e-300)
+    e = torch.floor(torch.log2(amax)) - 2.0
+    if not saturate:
+        e = torch.where(amax / torch.exp2(e) > 6.0, e + 1.0, e)
+    q = (b / torch.exp2(e)).clamp(-6.0, 6.0)
+    grid = _E2M1.double()
+    idx = (q.abs().unsqueeze(-1) - grid).abs().argmin(dim=-1)          # nearest grid point (ties: the lower index)
+    out = torch.sign(q) * grid[idx] * torch.exp2(e)
+    return out.reshape(*t.shape[:-1], -1)[..., :k]
+
+
+def make_mm_f16mx4(saturate: bool = True):
+    def mm(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+        """a [m,k] @ b [k,n]: fp16 x fp16 dominant term + two cross terms whose four planes are MXFP4 along k."""
+        a, b = a.float(), b.float()
+        ah, bh = a.half().float(), b.half().float()
+        al, bl = (a - ah), (b - bh)                                        # block scaling needs no 2^11 shift
+        q = lambda t: mxfp4(t, saturate=saturate)
+        bt, blt = b.T.contiguous(), bl.T.contiguous()                      # blocks run along k for both operands
+        cross = q(al) @ q(bt).T + q(a) @ q(blt).T
+        return ah.double() @ bh.double() + cross
+    return mm

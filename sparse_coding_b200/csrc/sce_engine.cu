@@ -747,6 +747,10 @@ static int run_pipeline_t(sce_plan* p, const float* x, int B, float* x_hat, bool
     zp.l1_over_b = p->l1_over_b;
     zp.db_part = p->b.encoder_bias ? p->db_part : nullptr;
     zp.tiles_m = tiles_mB;
+    zp.planes = p->dw_passes >= 3 ? 3 : 0;
+    // the only reader of dz's value plane is the dz^T x term of the weight gradient, against x's residual plane
+    // (per-model batches carry one flag for all of them, so the same test holds)
+    zp.x_res_flag = f8 ? p->res_flags : nullptr;
     rc = launch_k<EpiDco, false, false, AR>(n > 128, p->bk_dcode, pair_ok(p->pair_dcode, B, n), p, maps->dcode, 1, one, one, dd,
                                             p->dcode_passes, B, n, zp, st);
     if (rc) return rc;

@@ -55,17 +55,19 @@ __device__ __forceinline__ void stage_row32_u8(uint8_t* tile, int lane, const ui
 // whole warp: wait until the previous tiles have been read out, write the new ones, launch their stores.
 // bf16x3: whi / wx are the hi / lo planes. f16f8: whi is the fp16 plane, wx[0..7] the value-e5m2 plane and
 // wx[8..15] the residual-e5m2 plane (maps m_lo / m_x8).
+// `planes`: which of the f16f8 8-bit planes a consumer will read (bit 0: value plane, bit 1: residual plane); planes
+// nobody reads are neither staged nor stored (warp-uniform). bf16x3 always writes both of its planes.
 template <int ARITH>
 __device__ __forceinline__ void stage_and_store(uint8_t* stage, int lane, const uint32_t (&whi)[16],
                                                 const uint32_t (&wx)[16], const CUtensorMap* m_hi,
                                                 const CUtensorMap* m_lo, const CUtensorMap* m_x8, int col, int row0,
-                                                int model) {
+                                                int model, int planes = 3) {
   if (lane == 0) tma_store_wait_read();
   __syncwarp();
   stage_row32(stage, lane, whi);
   if constexpr (ARITH == kArithF16F8) {
-    stage_row32_u8(stage + 2048, lane, &wx[0]);
-    stage_row32_u8(stage + 3072, lane, &wx[8]);
+    if (planes & 1) stage_row32_u8(stage + 2048, lane, &wx[0]);
+    if (planes & 2) stage_row32_u8(stage + 3072, lane, &wx[8]);
   } else {
     stage_row32(stage + 2048, lane, wx);
   }
@@ -73,8 +75,12 @@ __device__ __forceinline__ void stage_and_store(uint8_t* stage, int lane, const 
   __syncwarp();
   if (lane == 0) {
     tma_store_3d(m_hi, stage, col, row0, model);
-    tma_store_3d(m_lo, stage + 2048, col, row0, model);
-    if constexpr (ARITH == kArithF16F8) tma_store_3d(m_x8, stage + 3072, col, row0, model);
+    if constexpr (ARITH == kArithF16F8) {
+      if (planes & 1) tma_store_3d(m_lo, stage + 2048, col, row0, model);
+      if (planes & 2) tma_store_3d(m_x8, stage + 3072, col, row0, model);
+    } else {
+      tma_store_3d(m_lo, stage + 2048, col, row0, model);
+    }
     tma_store_commit();
   }
 }
@@ -333,12 +339,18 @@ struct EpiDcodeT {
     const float* l1_over_b;        // [M]: alpha_m / B (f16f8: alpha_m d / 2, see EpiDecodeT)
     float* db_part;                // [M][tiles_m*4][n] or nullptr (no bias)
     int tiles_m;
+    // f16f8: the 8-bit planes of dz the weight-gradient GEMM will read. dz meets x there (dz^T x): its value plane
+    // multiplies x's RESIDUAL plane, which is all zeros for fp16-exact activations (*x_res_flag == 0: that cross term
+    // is skipped, GemmParams::b_res_flag) — and with single-pass backward GEMMs neither 8-bit plane is read at all.
+    const uint32_t* x_res_flag;    // device flag written by the batch split, or nullptr (unknown: write the plane)
+    int planes;                    // planes the consumer reads at most (3, or 0 with single-pass backward)
   };
   const Params& P;
   const TileCoord& T;
   int m_total, n_total;
   uint8_t* stage;
   float aB;
+  int planes;              // 8-bit planes of dz to write (see Params)
   uint32_t pos_n, zero_n;  // the mask words of this warp's next chunk, fetched one chunk ahead
   __device__ __forceinline__ void fetch_mask(int c) {
     const int col = T.col0 + c;
@@ -352,6 +364,8 @@ struct EpiDcodeT {
   __device__ EpiDcodeT(const Params& p, const TileCoord& t, int m, int n, uint8_t* st)
       : P(p), T(t), m_total(m), n_total(n), stage(st) {
     aB = __ldg(P.l1_over_b + T.model);
+    planes = P.planes;
+    if (P.x_res_flag && __ldg(P.x_res_flag) == 0u) planes &= ~1;
     fetch_mask(T.grp * 32);
   }
 
@@ -383,7 +397,7 @@ struct EpiDcodeT {
       }
     }
     stage_and_store<ARITH>(stage, T.lane, whi, wlo, &P.out_hi, &P.out_lo, &P.out_x8, col,
-                           T.m_blk * kBM + T.warp_q * 32, T.model);
+                           T.m_blk * kBM + T.warp_q * 32, T.model, planes);
     if (P.db_part && T.m_blk * kBM < m_total) {  // warp-uniform
       // transpose-reduce: 32 lanes x 32 columns -> lane j holds the sum of column j (31 shuffles)
 #pragma unroll
