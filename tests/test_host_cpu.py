@@ -269,3 +269,21 @@ def test_permutation_cache_changes_nothing():
         assert len(plain) == len(cached) == len(ref) == -(-n // 64)
         assert all(torch.equal(a, b) and torch.equal(a, c) for a, b, c in zip(plain, cached, ref))
     assert 1 <= len(cache) <= 4
+
+
+def test_chunk_file_record_offset(tmp_path):
+    """ChunkStreamer reads a chunk's bytes with read() straight into pinned memory when the file is a plain
+    torch.save of one contiguous tensor (the reference's {i}.pt format): the data record's offset must point at
+    exactly the tensor's bytes; anything else (several storages, a view of a larger storage) reports None -> mmap path."""
+    from sparse_coding_b200.train_loop import _single_record_offset
+    t = torch.randn(513, 40).half()
+    p = str(tmp_path / "0.pt")
+    torch.save(t, p)
+    off = _single_record_offset(p, t.numel() * 2)
+    raw = open(p, "rb").read()
+    assert off is not None and torch.equal(torch.frombuffer(bytearray(raw[off:off + t.numel() * 2]), dtype=torch.float16).view(513, 40), t)
+    torch.save([t, t + 1], p)
+    assert _single_record_offset(p, t.numel() * 2) is None
+    torch.save(t[:7], p)
+    assert _single_record_offset(p, 7 * 40 * 2) is None
+    assert _single_record_offset(str(tmp_path / "missing.pt"), 16) is None
