@@ -377,10 +377,18 @@ __global__ void __launch_bounds__(256) topk_sparse_kernel(TopkLists lists, const
   int cnt = (int)min((long long)min(n, kmax), __ldg(sparsity + model));
   // ---- gather: entry j, 16-byte piece q of its slice; every thread reads the column of its entry itself (one
   // dependent global load before the copies are in flight, not two), values and the x row are fetched alongside
-  for (int t = threadIdx.x; t < cnt * groups; t += 256) {
-    const int j = t / groups, q = t - j * groups;
-    const int col = __ldg(lists.col + lrow * kmax + j);
-    cp_async16(s_w + (size_t)j * ds + 4 * q, wn + ((long long)model * n + col) * d + (long long)slice * ds + 4 * q);
+  // (warp per entry: ONE column load and one base address per dictionary row, lanes stride its 16-byte pieces — the first
+  //  version spread the pieces over all threads and paid an integer division, 64-bit address arithmetic and a dependent
+  //  column load per PIECE: 43 % of the kernel's instructions, ncu source view of profiles/r02f_topk_full)
+  {
+    const float* wn_slice = wn + (long long)model * n * d + (long long)slice * ds;
+    const int* cols = lists.col + lrow * kmax;
+#pragma unroll 4
+    for (int j = warp; j < cnt; j += 8) {
+      const float* src = wn_slice + (long long)__ldg(cols + j) * d;
+      float* dst = s_w + (size_t)j * ds;
+      for (int q = lane; q < groups; q += 32) cp_async16(dst + 4 * q, src + 4 * q);
+    }
   }
   for (int j = threadIdx.x; j < cnt; j += 256) s_val[j] = __ldg(lists.val + lrow * kmax + j);
   float4 xv_pre = make_float4(0.f, 0.f, 0.f, 0.f);   // (groups <= 128 < 256 threads: one column group per thread)
