@@ -88,3 +88,118 @@ def test_harvest_on_gpu_then_train(tmp_path):
     dicts = train_on_chunks(ens, {"device": "cuda", "dict_size": 128}, folder, str(tmp_path / "sweep"), 64,
                             ["dict_size"], ["l1_alpha"], chunk_order=[0, 1, 2, 3])
     assert len(dicts) == 2 and all(torch.isfinite(ld.encoder).all() for ld, _ in dicts)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Golden fixtures written by the REFERENCE's own make_activation_dataset_tl / make_activation_dataset
+# (oracle/make_harvest_golden.py): chunk boundaries, flattening, first-chunk centring, the baukit GELU.
+# The language model's forward pass is recomputed here, so values are compared to one fp16 ulp (a different CPU or
+# the GPU may round an fp32 activation to the neighbouring fp16 value); shapes and chunk counts must match exactly.
+# ----------------------------------------------------------------------------------------------------------------------
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "harvest.pt")
+TL_CASES = ["tl_resid", "tl_resid_centred", "tl_mlp_skip1", "tl_attn_concat"]
+SINGLE_CASES = ["single_tl", "single_tl_centred", "single_baukit", "single_baukit_centred", "single_tl_2chunks"]
+
+
+def _fixture(device):
+    pytest.importorskip("transformers")
+    from oracle import harvest_models as HM
+    fx = torch.load(GOLDEN)
+    lm = HM.tiny_neox()
+    lm.load_state_dict(fx["lm_state"])
+    nano = HM.TinyNano()
+    nano.load_state_dict(fx["nano_state"])
+    rows = [{"input_ids": t} for t in fx["tokens"]]
+    loader = torch.utils.data.DataLoader(rows, batch_size=fx["model_batch_size"], shuffle=False)
+    return fx, HM.TinyHooked(lm).to(device), nano.to(device), loader
+
+
+def _read(folder):
+    files = sorted(os.listdir(folder), key=lambda f: int(f[:-3]))
+    assert files == [f"{i}.pt" for i in range(len(files))]
+    return [torch.load(os.path.join(folder, f)) for f in files]
+
+
+def _same_chunks(got, want):
+    assert [tuple(t.shape) for t in got] == [tuple(t.shape) for t in want]
+    for g, w in zip(got, want):
+        assert g.dtype == w.dtype == torch.float16 and g.is_contiguous()
+        assert g.untyped_storage().nbytes() == g.numel() * 2          # compact file, also for undersized chunks
+        torch.testing.assert_close(g.float(), w.float(), rtol=2e-3, atol=2e-4)
+
+
+def _tl_case(tag, device, tmp_path):
+    from sparse_coding_b200.harvest import make_activation_dataset_tl
+    fx, hooked, _, loader = _fixture(device)
+    c = fx["cases"][tag]
+    folders = [str(tmp_path / tag / str(l)) for l in c["layers"]]
+    n_act = make_activation_dataset_tl(loader, hooked, c["activation_width"], folders, layers=c["layers"],
+                                       tensor_loc=c["tensor_loc"], chunk_size_gb=c["chunk_size_gb"],
+                                       device=torch.device(device), n_chunks=c["n_chunks"], max_length=fx["max_length"],
+                                       model_batch_size=fx["model_batch_size"], skip_chunks=c["skip_chunks"],
+                                       center_dataset=c["center_dataset"])
+    assert n_act == c["n_activations"]
+    for folder, want in zip(folders, c["chunks"]):
+        _same_chunks(_read(folder), want)
+
+
+def _single_case(tag, device, tmp_path):
+    from sparse_coding_b200.harvest import make_activation_dataset
+    fx, hooked, nano, loader = _fixture(device)
+    c = fx["cases"][tag]
+    folder = str(tmp_path / tag)
+    make_activation_dataset(loader, nano if c["baukit"] else hooked, c["tensor_name"], c["activation_width"], folder,
+                            baukit=c["baukit"], chunk_size_gb=c["chunk_size_gb"], device=torch.device(device),
+                            layer=c["layer"], n_chunks=c["n_chunks"], max_length=fx["max_length"],
+                            model_batch_size=fx["model_batch_size"], center_dataset=c["center_dataset"])
+    _same_chunks(_read(folder), c["chunks"])
+
+
+@pytest.mark.parametrize("tag", TL_CASES)
+def test_tl_harvest_matches_reference_files_cpu(tag, tmp_path):
+    _tl_case(tag, "cpu", tmp_path)
+
+
+@pytest.mark.parametrize("tag", SINGLE_CASES)
+def test_single_tensor_harvest_matches_reference_files_cpu(tag, tmp_path):
+    _single_case(tag, "cpu", tmp_path)
+
+
+def test_tensor_names_match_reference():
+    from sparse_coding_b200.harvest import make_tensor_name
+    from oracle import harvest_models as HM
+    fx = torch.load(GOLDEN)
+    for loc in ("residual", "mlp", "attn", "attn_concat", "mlpout"):
+        assert make_tensor_name(3, loc, HM.TINY_TL_NAME) == fx["tensor_names"][loc]
+    assert make_tensor_name(3, "mlp", "nanoGPT") == fx["tensor_names"]["mlp_nanoGPT"]
+    with pytest.raises(NotImplementedError):
+        make_tensor_name(3, "residual", "nanoGPT")
+    with pytest.raises(AssertionError):
+        make_tensor_name(3, "nowhere", HM.TINY_TL_NAME)
+
+
+def test_tl_harvest_stops_cleanly_on_a_chunk_boundary(tmp_path):
+    """8 model batches in chunks of 3 + 1: the reference goes on to torch.cat([]) (activation_dataset.py:382, :500);
+    here the run ends after the two full chunks."""
+    from sparse_coding_b200.harvest import make_activation_dataset_tl
+    fx, hooked, _, _ = _fixture("cpu")
+    rows = [{"input_ids": t} for t in fx["tokens"][:32]]
+    loader = torch.utils.data.DataLoader(rows, batch_size=4, shuffle=False)
+    c = fx["cases"]["tl_resid"]
+    folder = str(tmp_path / "b")
+    n = make_activation_dataset_tl(loader, hooked, c["activation_width"], [folder], layers=[1],
+                                   chunk_size_gb=c["chunk_size_gb"], device=torch.device("cpu"), n_chunks=5,
+                                   max_length=fx["max_length"], model_batch_size=4)
+    assert n == 32 * fx["max_length"] and [t.shape[0] for t in _read(folder)] == [256, 256]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag", ["tl_resid_centred", "tl_attn_concat"])
+def test_tl_harvest_matches_reference_files_gpu(tag, tmp_path):
+    _tl_case(tag, "cuda", tmp_path)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag", ["single_tl_centred", "single_baukit_centred"])
+def test_single_tensor_harvest_matches_reference_files_gpu(tag, tmp_path):
+    _single_case(tag, "cuda", tmp_path)
