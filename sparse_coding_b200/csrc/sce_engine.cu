@@ -77,6 +77,8 @@ struct sce_plan {
   __nv_bfloat16 *dz_hi, *dz_lo;   // [M, Bmax, n]   (top-k: fp32 scores alias these planes)
   uint8_t *x_x8, *wenc_x8, *wdec_x8, *c_x8, *g_x8, *dz_x8;
   float* scores;                  // top-k: fp32 scores [M, Bmax, n] of the encode GEMM
+  uint32_t* tk_cmax;              // top-k: largest key per 32-column chunk of the scores [M, Bmax, n_chunks] (EpiScoresTma)
+  int topk_cmax;                  // 1: the selection works from the chunk maxima (SCE_TOPK_CMAX=0 turns it off)
   int *tk_col, *tk_cnt;           // top-k lists (TopkLists): selected columns [M, Bmax, kmax], entries per row [M, Bmax]
   float *tk_val, *tk_dots;        // their values [M, Bmax, kmax]; per-slice shares of g . W_j [M, Bmax, kmax, slices]
   float* wn_f32;                  // top-k: fp32 copy of the normalised dictionary [M, n, d] the gather kernel reads
@@ -228,8 +230,10 @@ static size_t carve(sce_plan* p, const sce_desc& d, uint8_t* base) {
   float* sc = nullptr;
   int *tkc = nullptr, *tkn = nullptr;
   float *tkv = nullptr, *tkd = nullptr, *wnf = nullptr;
+  uint32_t* tcm = nullptr;
   if (d.variant == SCE_TOPK) {
     sc = c.take<float>(M * B * n);
+    tcm = c.take<uint32_t>(M * B * n_chunks);
     if (kmax) {
       tkc = c.take<int>(M * B * kmax);
       tkv = c.take<float>(M * B * kmax);
@@ -270,6 +274,7 @@ static size_t carve(sce_plan* p, const sce_desc& d, uint8_t* base) {
     p->nnz_stage = ns;
     p->res_flags = rf;
     p->scores = sc;
+    p->tk_cmax = tcm;
     p->tk_col = tkc;
     p->tk_val = tkv;
     p->tk_cnt = tkn;
@@ -656,6 +661,11 @@ static int run_pipeline_t(sce_plan* p, const float* x, int B, float* x_hat, bool
     // scores -> fp32, then per-row selection (code planes, activity mask, k-sparse lists)
     EpiScoresTma::Params sp;
     sp.out = maps->st_scores;
+    if (p->topk_cmax) {
+      sp.cmax = p->tk_cmax;
+      sp.n_chunks = act.n_chunks;
+      sp.cmax_model_stride = (long long)Bm * act.n_chunks;
+    }
     rc = launch_k<EpiScoresTma, false, false, AR>(n > 128, p->bk_encode, pair_ok(p->pair_encode, B, n), p, maps->encode, 1, xb,
                                                  one, dd, d.fwd_passes, B, n, sp, st, x_is_a);
     if (rc) return rc;
@@ -673,7 +683,7 @@ static int run_pipeline_t(sce_plan* p, const float* x, int B, float* x_hat, bool
     // one block per (row, model); scores / codes of model m start at m * batch_max * n
     topk_select2_kernel<AR><<<dim3(B, M), 256, 0, st>>>(
         p->scores, p->b.sparsity, p->c_hi, p->c_lo, p->c_x8, p->topk_sparse ? (void*)p->dz_hi : nullptr, p->dz_lo, p->dz_x8,
-        act, tk, p->part_enc, B, n, Bm * n);
+        act, tk, p->part_enc, B, n, Bm * n, p->topk_cmax ? p->tk_cmax : nullptr);
     ++launches;
     CUDA_TRY(cudaGetLastError());
     n_enc_parts = B;
@@ -895,6 +905,8 @@ int sce_plan_create(const sce_desc* desc, const sce_buffers* buffers, sce_plan**
     // SCE_TOPK_SPARSE = 1 / 0 forces it on / off.
     const int heuristic = (long long)desc->n >= 160ll * (long long)(kmax ? kmax : 1);
     p->topk_sparse = desc->variant == SCE_TOPK && kmax > 0 && p->tk_slices > 0 && tune_flag("SCE_TOPK_SPARSE", heuristic);
+    // selection from the per-chunk maxima the scores epilogue writes (profiles/r02p_*); 0 = read every row twice as before
+    p->topk_cmax = desc->variant == SCE_TOPK && tune_flag("SCE_TOPK_CMAX", 1);
   }
   p->maps = new std::map<int, BatchMaps*>();
   carve(p, *desc, static_cast<uint8_t*>(b.workspace));

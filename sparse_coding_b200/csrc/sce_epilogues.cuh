@@ -431,6 +431,11 @@ struct EpiScoresTma {
   static constexpr int kWarpStageBytes = 4096;
   struct Params {
     CUtensorMap out;   // [M][B][n] fp32, box 32 x 32
+    // optional: largest order-preserving key (f2key) of every 32-column chunk of every row, [M][batch_max][n_chunks] —
+    // the selection then reads these (1/32 of the scores) and only the chunks that can hold one of the k largest
+    uint32_t* cmax = nullptr;
+    int n_chunks = 0;
+    long long cmax_model_stride = 0;   // batch_max * n_chunks
   };
   const Params& P;
   const TileCoord& T;
@@ -452,6 +457,18 @@ struct EpiScoresTma {
     if (T.lane == 0) {
       tma_store_3d(&P.out, stage, col, T.m_blk * kBM + T.warp_q * 32, T.model);
       tma_store_commit();
+    }
+    if (P.cmax) {   // (kernel-uniform)
+      const int valid = n_total - col;   // columns of this chunk inside the matrix (a multiple of 8)
+      uint32_t mx = 0;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const uint32_t u = r[j];
+        const uint32_t key = u ^ ((uint32_t)((int32_t)u >> 31) | 0x80000000u);   // == f2key
+        if (valid >= 32 || j < valid) mx = max(mx, key);
+      }
+      if (T.row < m_total)
+        P.cmax[(long long)T.model * P.cmax_model_stride + (long long)T.row * P.n_chunks + (col >> 5)] = mx;
     }
   }
   __device__ __forceinline__ void finish() {

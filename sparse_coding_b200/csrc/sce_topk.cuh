@@ -96,6 +96,7 @@ struct TopkLists {
 //   5. scatter the k entries into the zeroed planes, activity-mask bits, (column, value) list, per-row partials
 // ------------------------------------------------------------------------------------------------
 constexpr int kTopkCand = 1024;
+constexpr int kTopkChunkList = 2048;   // 32-column chunks of a row the chunk-maxima path can list (n <= 65536)
 
 template <int ARITH>
 __global__ void __launch_bounds__(256) topk_select2_kernel(const float* __restrict__ scores,
@@ -105,8 +106,11 @@ __global__ void __launch_bounds__(256) topk_select2_kernel(const float* __restri
                                                            void* __restrict__ dz_lo, void* __restrict__ dz_x8,
                                                            ActMask act, TopkLists lists,
                                                            float* __restrict__ part /*[M][B][2]*/, int B, int n,
-                                                           long long model_stride /*elements between models*/) {
+                                                           long long model_stride /*elements between models*/,
+                                                           const uint32_t* __restrict__ cmax /*[M][batch_max][n_chunks] or nullptr*/) {
   constexpr int UNROLL = 4;
+  __shared__ uint16_t chunk_list[kTopkChunkList];
+  __shared__ uint32_t sh_nchunk;
   __shared__ uint32_t cand_key[kTopkCand];
   __shared__ int cand_col[kTopkCand];
   __shared__ uint32_t hist[256];
@@ -124,7 +128,16 @@ __global__ void __launch_bounds__(256) topk_select2_kernel(const float* __restri
     sh_ncand = 0;
     sh_kept = 0;
     sh_ties = 0;
+    sh_nchunk = 0;
   }
+  // Chunk maxima from the scores epilogue (EpiScoresTma): chunk i belongs to thread i % 256, so the first
+  // n_chunks / 32 warps hold a real element of the row in every lane. The bound below is then taken over those warps
+  // only: `full_warps` warps x their j-th largest maximum, j = ceil(k / full_warps) <= 32, are >= k elements.
+  const int n_chunks = act.n_chunks;
+  const int full_warps = min(8, n_chunks >> 5);
+  const int j_pick = full_warps ? (k + full_warps - 1) / full_warps : 33;
+  const bool fused = cmax != nullptr && k <= 256 && j_pick <= 32 && n_chunks <= kTopkChunkList;   // block-uniform
+  const uint32_t* cm = fused ? cmax + ((long long)model * act.batch_max + row) * n_chunks : nullptr;
   // ---- 1. first pass over the row: per-thread maximum; meanwhile clear this row of the outputs
   uint32_t my_max = 0;
   const float4* src4 = reinterpret_cast<const float4*>(scores + base);
@@ -132,6 +145,9 @@ __global__ void __launch_bounds__(256) topk_select2_kernel(const float* __restri
     const float4 v = __ldg(src4 + i);
     return make_uint4(f2key(v.x), f2key(v.y), f2key(v.z), f2key(v.w));
   };
+  if (fused) {
+    for (int i = threadIdx.x; i < n_chunks; i += 256) my_max = max(my_max, __ldg(cm + i));
+  } else
   for (int i0 = 0; i0 < n4; i0 += 256 * UNROLL) {
     float4 v[UNROLL];
 #pragma unroll
@@ -175,16 +191,46 @@ __global__ void __launch_bounds__(256) topk_select2_kernel(const float* __restri
         v = up ? max(v, o) : min(v, o);
       }
     }
-    const int j = (k + 7) >> 3;   // 8 warps x j elements >= their j-th largest: at least k elements >= the minimum
+    // 8 warps x j elements >= their j-th largest: at least k elements >= the minimum (fused: the full warps only)
+    const int j = fused ? j_pick : (k + 7) >> 3;
     if (lane == j - 1) warp_bound[warp] = v;
   }
   __syncthreads();
   if (k <= 256) {
+    const int nw = fused ? full_warps : 8;
     bound = warp_bound[0];
-#pragma unroll
-    for (int w = 1; w < 8; ++w) bound = min(bound, warp_bound[w]);
+    for (int w = 1; w < nw; ++w) bound = min(bound, warp_bound[w]);
   }
-  // ---- 3. candidates (second pass over the row, L2-resident)
+  // ---- 3. candidates
+  if (fused) {
+    // only the chunks whose maximum reaches the bound can hold a candidate: list them, then a warp per listed chunk
+    // reads its 128 bytes (four chunks in flight per warp)
+    for (int i = threadIdx.x; i < n_chunks; i += 256)
+      if (__ldg(cm + i) >= bound) chunk_list[atomicAdd(&sh_nchunk, 1u)] = (uint16_t)i;
+    __syncthreads();
+    const int nch = (int)sh_nchunk;
+    for (int c0 = warp * 4; c0 < nch; c0 += 32) {
+      float v[4];
+      int col[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        col[u] = c0 + u < nch ? (int)chunk_list[c0 + u] * 32 + lane : n;
+        v[u] = col[u] < n ? __ldg(scores + base + col[u]) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t kv = f2key(v[u]);
+        if (col[u] < n && kv >= bound) {
+          const uint32_t slot = atomicAdd(&sh_ncand, 1u);
+          if (slot < kTopkCand) {
+            cand_key[slot] = kv;
+            cand_col[slot] = col[u];
+          }
+        }
+      }
+    }
+  } else
+  // (second pass over the row, L2-resident)
   for (int i0 = 0; i0 < n4; i0 += 256 * UNROLL) {
     float4 v[UNROLL];
 #pragma unroll

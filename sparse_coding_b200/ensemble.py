@@ -35,6 +35,7 @@ import torch
 from . import _lib
 from .optim import AdamConfig, adam, resolve_optimizer
 from .signatures import DictSignature
+from .tracing import nvtx_range
 
 Tensor = torch.Tensor
 
@@ -378,7 +379,7 @@ class FunctionalEnsemble:
     # ------------------------------------------------------------------------------------------------------
     def step_batch(self, minibatches, expand_dims=True):
         """One Adam step of every model on one batch (ensemble.py:175-193). Returns (loss_data, aux)."""
-        with torch.no_grad():
+        with torch.no_grad(), nvtx_range("sce.step_batch"):
             every = getattr(self, "health_check_every", 64)
             while True:
                 x, B = self._prep_batch(minibatches, expand_dims)

@@ -22,6 +22,7 @@ import numpy as np
 import torch
 
 from . import _lib
+from .tracing import nvtx_range
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -296,6 +297,10 @@ class ChunkStreamer:
         return t.contiguous(), path, offset
 
     def _stage(self, slot: int, chunk_idx: int):
+        with nvtx_range(f"sce.stage_chunk {chunk_idx}"):
+            return self._stage_impl(slot, chunk_idx)
+
+    def _stage_impl(self, slot: int, chunk_idx: int):
         import time
         t0 = time.perf_counter()
         torch.cuda.set_device(self.device)
@@ -453,16 +458,18 @@ def train_on_chunks(ensemble, args: dict, dataset_folder: str, output_folder: st
         torch.set_grad_enabled(False)
         torch.manual_seed(0)
         np.random.seed(0)
-        for j, idx in enumerate(_batch_index_lists(sampler, device, perm_cache)):
-            batch = gather_rows(chunk, idx, sub=means)
-            ensemble.step_batch(batch)
+        with nvtx_range(f"sce.chunk {chunk_idx}"):
+            for j, idx in enumerate(_batch_index_lists(sampler, device, perm_cache)):
+                batch = gather_rows(chunk, idx, sub=means)
+                ensemble.step_batch(batch)
         check_input_range(ensemble)
         if on_chunk_end is not None:
             on_chunk_end(i, chunk_idx, ensemble)      # e.g. the end-of-chunk metric gather (sharding.gather_metrics)
         last = i == len(chunk_order) - 1
         if last or (save_schedule == "sweep" and (i + 1) in [2 ** j for j in range(3, 10)]) or save_schedule == "every":
             # export (a full D2H of the parameters, which also drains the GPU) only when a checkpoint is due
-            learned_dicts = unstacked_to_learned_dicts(ensemble, args, ensemble_hyperparams, buffer_hyperparams)
+            with nvtx_range("sce.export_learned_dicts"):
+                learned_dicts = unstacked_to_learned_dicts(ensemble, args, ensemble_hyperparams, buffer_hyperparams)
             it_folder = os.path.join(output_folder, f"_{i}")
             os.makedirs(it_folder, exist_ok=True)
             torch.save(learned_dicts, os.path.join(it_folder, "learned_dicts.pt"))

@@ -353,6 +353,7 @@ def test_config2_shape_properties():
     # (kind, M, d, n, B)  — the non-headline BASELINE configs at their real widths, reduced batch
     ("topk", 3, 768, 3072, 512),      # config 3: GPT-2-small residual, TopK k in {16, 32, 64}
     ("topk", 2, 768, 12288, 256),     # config 3: largest dictionary
+    ("topk", 3, 128, 1040, 200),      # 32.5 chunks of 32 columns: one full warp of chunk maxima, a half chunk at the end
     ("topk", 1, 256, 32768, 128),     # rows too long for the candidate list in shared memory (keys-only select)
     ("tied", 1, 2048, 32768, 256),    # config 5: Pythia-1.4b MLP-out, dict_ratio 16
     ("untied", 2, 768, 3072, 384),    # untied at GPT-2 width

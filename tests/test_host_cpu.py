@@ -287,3 +287,18 @@ def test_chunk_file_record_offset(tmp_path):
     torch.save(t[:7], p)
     assert _single_record_offset(p, 7 * 40 * 2) is None
     assert _single_record_offset(str(tmp_path / "missing.pt"), 16) is None
+
+
+def test_nvtx_ranges_are_off_by_default_and_switchable(monkeypatch):
+    """SURVEY §5 tracing: SCE_NVTX=1 turns the ranges on at import; by default a range is a no-op context."""
+    import contextlib
+    import importlib
+    import sparse_coding_b200.tracing as tr
+    monkeypatch.delenv("SCE_NVTX", raising=False)
+    tr = importlib.reload(tr)
+    assert tr.ENABLED is False and isinstance(tr.nvtx_range("x"), contextlib.nullcontext)
+    monkeypatch.setenv("SCE_NVTX", "1")
+    tr = importlib.reload(tr)
+    assert tr.ENABLED is True and not isinstance(tr.nvtx_range("x"), contextlib.nullcontext)
+    monkeypatch.delenv("SCE_NVTX", raising=False)
+    importlib.reload(tr)
