@@ -97,6 +97,7 @@ struct sce_plan {
   int split_decode;  // 1: separate TMEM accumulators for hi*hi and the cross terms in the decode GEMM (default)
   int pair_encode, pair_decode, pair_dcode, pair_dw;  // 1: run that GEMM on CTA pairs (cta_group::2, 256-row tiles)
   int bk_encode, bk_decode, bk_dcode;  // K block (64: 128-byte swizzle, 32: 64-byte swizzle) of the K-major GEMMs
+  int dw_collector;  // NSUB = 2 tiles: A slice kept in the tensor core's collector across the two column halves (SCE_TUNE_DW_COLL)
   int dw_nsub2;      // f16f8 weight gradient: 256 x 512 tiles sharing one A tile (env SCE_TUNE_DW_NSUB2 = 0 switches it off)
   int last_launches;
   long long step;  // number of optimiser steps taken
@@ -132,7 +133,7 @@ static int validate(const sce_desc* d) {
   if (d->n_models < 1 || d->batch_max < 1) return fail(SCE_ERR_INVALID, "n_models and batch_max must be >= 1");
   if (d->d < 8 || d->d % 8 || d->n < 8 || d->n % 8)
     return fail(SCE_ERR_INVALID, "d (%d) and n (%d) must be positive multiples of 8", d->d, d->n);
-  if (d->d > 2048) return fail(SCE_ERR_INVALID, "d = %d > 2048 is not supported by the row kernels", d->d);
+  if (d->d > 8192) return fail(SCE_ERR_INVALID, "d = %d > 8192 is not supported by the row kernels", d->d);
   if ((d->fwd_passes != 1 && d->fwd_passes != 3) || (d->bwd_passes != 1 && d->bwd_passes != 3))
     return fail(SCE_ERR_INVALID, "fwd_passes / bwd_passes must be 1 or 3");
   if (d->arith < SCE_ARITH_AUTO || d->arith > SCE_ARITH_F16F8) return fail(SCE_ERR_INVALID, "unknown arith %d", d->arith);
@@ -469,6 +470,7 @@ static int launch_gemm_t(const sce_plan* p, const GemmMaps& maps, int nsets, con
   gp.tiles_m = (m_total + kTileRows - 1) / kTileRows;
   gp.tiles_n = (n_total + NSUB * BN - 1) / (NSUB * BN);
   gp.epi = epi;
+  gp.a_collector = p->dw_collector;
   const int units = CTA2 ? p->sms / 2 : p->sms;     // persistent: one CTA (or CTA pair) per SM (pair)
   int tiles = gp.n_models * gp.tiles_m * gp.tiles_n;
   if constexpr (NSUB == 2) {
@@ -553,8 +555,12 @@ static int launch_dict_rows_t(float* e, const float* dw, float* m, float* v, voi
     dict_rows_kernel<1, MODE, ARITH><<<(unsigned)rows, 128, 0, st>>>(e, dw, m, v, hi, lo, x8, grad_out, d, normalize, floor, h, health, w_f32);
   else if (nv == 2)
     dict_rows_kernel<2, MODE, ARITH><<<(unsigned)rows, 128, 0, st>>>(e, dw, m, v, hi, lo, x8, grad_out, d, normalize, floor, h, health, w_f32);
-  else
+  else if (nv <= 4)
     dict_rows_kernel<4, MODE, ARITH><<<(unsigned)rows, 128, 0, st>>>(e, dw, m, v, hi, lo, x8, grad_out, d, normalize, floor, h, health, w_f32);
+  else if (nv <= 8)    // d <= 4096 (Pythia-6.9b residual width)
+    dict_rows_kernel<8, MODE, ARITH><<<(unsigned)rows, 128, 0, st>>>(e, dw, m, v, hi, lo, x8, grad_out, d, normalize, floor, h, health, w_f32);
+  else                 // d <= 8192
+    dict_rows_kernel<16, MODE, ARITH><<<(unsigned)rows, 128, 0, st>>>(e, dw, m, v, hi, lo, x8, grad_out, d, normalize, floor, h, health, w_f32);
   CUDA_TRY(cudaGetLastError());
   return SCE_OK;
 }
@@ -885,6 +891,7 @@ int sce_plan_create(const sce_desc* desc, const sce_buffers* buffers, sce_plan**
   // at config 2, device time unchanged within the run-to-run noise (1.51 / 1.50 / 1.57 ms against 1.51 / 1.50 ms: the
   // kernel is bound by the power-limited tensor rate either way) — off by default, kept as a knob
   p->dw_nsub2 = tune_flag("SCE_TUNE_DW_NSUB2", 0);
+  p->dw_collector = tune_flag("SCE_TUNE_DW_COLL", 1);
   p->bk_encode = tune_bk("SCE_TUNE_BK_ENCODE", 64);
   p->bk_decode = tune_bk("SCE_TUNE_BK_DECODE", 32);
   p->bk_dcode = tune_bk("SCE_TUNE_BK_DCODE", 64);

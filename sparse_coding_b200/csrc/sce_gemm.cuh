@@ -59,6 +59,8 @@ struct GemmParams {
   // NSUB == 2 only: the last `tail_rows` row blocks (model-major order) are processed as single-width tiles, two per
   // row block, so that the final wave of the persistent grid is not half empty (requires tiles_n == 1). 0 = none.
   int tail_rows;
+  // NSUB == 2 only: issue the two MMAs of a K slice as collector::a::fill / ::lastuse (A read from shared memory once)
+  int a_collector;
   EpiParams epi;
 };
 
@@ -402,6 +404,26 @@ gemm_split_kernel(const __grid_constant__ GemmParams<typename Epi::Params> p) {
                 const uint64_t ah = make_sdesc(sa_h + k * a8_kstep, a_lbo, a8_sbo, a8_lt);
                 const uint64_t al = make_sdesc(sa_l + k * a8_kstep, a_lbo, a8_sbo, a8_lt);
                 uint32_t acc_after = accumulate;
+                if constexpr (NSUB == 2 && CTA2) {
+                  if (nsub == 2 && p.a_collector) {
+                    const uint32_t sub8 = uint32_t(SM::kBSub * BK);
+                    const uint64_t bh0 = make_sdesc(sb_h + k * b8_kstep, b_lbo, b8_sbo, b8_lt);
+                    const uint64_t bh1 = make_sdesc(sb_h + sub8 + k * b8_kstep, b_lbo, b8_sbo, b8_lt);
+                    const uint64_t bl0 = make_sdesc(sb_l + k * b8_kstep, b_lbo, b8_sbo, b8_lt);
+                    const uint64_t bl1 = make_sdesc(sb_l + sub8 + k * b8_kstep, b_lbo, b8_sbo, b8_lt);
+                    if (t_lh) {
+                      umma_f8_2cta_coll<1>(d_tmem, al, bh0, i8, accumulate);
+                      umma_f8_2cta_coll<2>(d_tmem + uint32_t(BN), al, bh1, i8, accumulate);
+                    }
+                    if (t_hl) {
+                      const uint32_t a2 = t_lh ? 1u : accumulate;
+                      umma_f8_2cta_coll<1>(d_tmem, ah, bl0, i8, a2);
+                      umma_f8_2cta_coll<2>(d_tmem + uint32_t(BN), ah, bl1, i8, a2);
+                    }
+                    accumulate = 1;
+                    continue;
+                  }
+                }
                 for (int sub = 0; sub < nsub; ++sub) {
                   const uint32_t sub8 = uint32_t(sub * (SM::kBSub * BK));   // bytes of one sub-tile's 8-bit plane
                   const uint64_t bh = make_sdesc(sb_h + sub8 + k * b8_kstep, b_lbo, b8_sbo, b8_lt);
@@ -436,6 +458,22 @@ gemm_split_kernel(const __grid_constant__ GemmParams<typename Epi::Params> p) {
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k) {
               const uint64_t ah = make_sdesc(sa + k * a_kstep, a_lbo, a_sbo, a_lt);
+              if constexpr (NSUB == 2 && CTA2) {
+                if (nsub == 2 && p.a_collector) {
+                  const uint64_t bh0 = make_sdesc(sb + k * b_kstep, b_lbo, b_sbo, b_lt);
+                  const uint64_t bh1 = make_sdesc(sb + uint32_t(SM::kBSub * BK * 2) + k * b_kstep, b_lbo, b_sbo, b_lt);
+                  if (k == 0 && rescale) {
+                    umma_f16_rescale_2cta_coll<1>(d_tmem, ah, bh0, i16);
+                    umma_f16_rescale_2cta_coll<2>(d_tmem + uint32_t(BN), ah, bh1, i16);
+                  } else {
+                    umma_f16_2cta_coll<1>(d_tmem, ah, bh0, i16, accumulate);
+                    umma_f16_2cta_coll<2>(d_tmem + uint32_t(BN), ah, bh1, i16, accumulate);
+                  }
+                  if (k == 0) rescale = false;
+                  accumulate = 1;
+                  continue;
+                }
+              }
               for (int sub = 0; sub < nsub; ++sub) {
                 const uint64_t bh = make_sdesc(sb + uint32_t(sub * (SM::kBSub * BK * 2)) + k * b_kstep, b_lbo, b_sbo, b_lt);
                 if (k == 0 && rescale) umma_f16_rescale<CTA2>(d_tmem + uint32_t(sub * BN), ah, bh, i16);  // D = ah*bh + D * 2^-kLoShift

@@ -314,6 +314,57 @@ __device__ __forceinline__ void umma_f16_rescale(uint32_t tmem_d, uint64_t adesc
 }
 
 // ----------------------------------------------------------------------------------------------
+// A-operand collector (tcgen05.mma ... .collector::a::fill / ::lastuse): two consecutive MMAs that multiply the SAME
+// A slice by different B sub-tiles (the 256 x 512 output tiles, NSUB = 2) read A from shared memory once — the first
+// keeps it in the tensor core's collector buffer (SASS: A_KEEP), the second takes it from there (A_REUSE). With 4-byte
+// operand planes the main loop otherwise needs more than the SM's 128 B/clk of shared-memory bandwidth.
+// COLL: 0 = default (discard), 1 = fill, 2 = lastuse. CTA pairs only (the only place NSUB = 2 is used).
+// ----------------------------------------------------------------------------------------------
+template <int COLL>
+__device__ __forceinline__ void umma_f8_2cta_coll(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if constexpr (COLL == 1) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::2.kind::f8f6f4.collector::a::fill [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+                 "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+  } else if constexpr (COLL == 2) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::2.kind::f8f6f4.collector::a::lastuse [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+                 "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+  } else {
+    umma_f8<true>(tmem_d, adesc, bdesc, idesc, accumulate);
+  }
+}
+template <int COLL>
+__device__ __forceinline__ void umma_f16_2cta_coll(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if constexpr (COLL == 1) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::2.kind::f16.collector::a::fill [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+                 "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+  } else if constexpr (COLL == 2) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::2.kind::f16.collector::a::lastuse [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+                 "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+  } else {
+    umma_bf16_2cta(tmem_d, adesc, bdesc, idesc, accumulate);
+  }
+}
+// D = A*B + D * 2^-kLoShift with the collector qualifier
+template <int COLL>
+__device__ __forceinline__ void umma_f16_rescale_2cta_coll(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
+  if constexpr (COLL == 1) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 1, 0;\n\t"
+                 "tcgen05.mma.cta_group::2.kind::f16.collector::a::fill [%0], %1, %2, %3, p, %4;\n\t}\n" ::"r"(tmem_d),
+                 "l"(adesc), "l"(bdesc), "r"(idesc), "n"(kLoShift) : "memory");
+  } else if constexpr (COLL == 2) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 1, 0;\n\t"
+                 "tcgen05.mma.cta_group::2.kind::f16.collector::a::lastuse [%0], %1, %2, %3, p, %4;\n\t}\n" ::"r"(tmem_d),
+                 "l"(adesc), "l"(bdesc), "r"(idesc), "n"(kLoShift) : "memory");
+  } else {
+    umma_f16_rescale<true>(tmem_d, adesc, bdesc, idesc);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
 // bf16 hi/lo split: x ~= hi + lo with hi = bf16(x), lo = bf16(x - hi); |x - hi - lo| <= 2^-17 |x|.
 // ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {

@@ -96,6 +96,11 @@ struct TopkLists {
 //   5. scatter the k entries into the zeroed planes, activity-mask bits, (column, value) list, per-row partials
 // ------------------------------------------------------------------------------------------------
 constexpr int kTopkCand = 1024;
+__device__ __forceinline__ unsigned long long pack_cand(uint32_t key, int col) {
+  return ((unsigned long long)key << 32) | (uint32_t)(0x7FFFFFFF - col);
+}
+__device__ __forceinline__ uint32_t cand_key_of(unsigned long long c) { return (uint32_t)(c >> 32); }
+__device__ __forceinline__ int cand_col_of(unsigned long long c) { return 0x7FFFFFFF - (int)(uint32_t)c; }
 constexpr int kTopkChunkList = 2048;   // 32-column chunks of a row the chunk-maxima path can list (n <= 65536)
 
 template <int ARITH>
@@ -111,8 +116,10 @@ __global__ void __launch_bounds__(256) topk_select2_kernel(const float* __restri
   constexpr int UNROLL = 4;
   __shared__ uint16_t chunk_list[kTopkChunkList];
   __shared__ uint32_t sh_nchunk;
-  __shared__ uint32_t cand_key[kTopkCand];
-  __shared__ int cand_col[kTopkCand];
+  // candidates as one 64-bit word: key in the high half, (0x7FFFFFFF - column) in the low half — a strict order in which
+  // "larger" means larger key, or equal key and lower column (ties go to the lowest column)
+  __shared__ unsigned long long cand[kTopkCand];
+  __shared__ int cand_rank[kTopkCand];
   __shared__ uint32_t hist[256];
   __shared__ uint32_t sh_prefix, sh_remaining, sh_ncand, sh_neq, sh_kept, sh_ties;
   __shared__ uint32_t warp_cnt[8], warp_cnt2[8], warp_bound[8];
@@ -222,10 +229,7 @@ __global__ void __launch_bounds__(256) topk_select2_kernel(const float* __restri
         const uint32_t kv = f2key(v[u]);
         if (col[u] < n && kv >= bound) {
           const uint32_t slot = atomicAdd(&sh_ncand, 1u);
-          if (slot < kTopkCand) {
-            cand_key[slot] = kv;
-            cand_col[slot] = col[u];
-          }
+          if (slot < kTopkCand) cand[slot] = pack_cand(kv, col[u]);
         }
       }
     }
@@ -247,10 +251,7 @@ __global__ void __launch_bounds__(256) topk_select2_kernel(const float* __restri
       for (int e = 0; e < 4; ++e)
         if (kv[e] >= bound) {
           const uint32_t slot = atomicAdd(&sh_ncand, 1u);
-          if (slot < kTopkCand) {
-            cand_key[slot] = kv[e];
-            cand_col[slot] = 4 * i + e;
-          }
+          if (slot < kTopkCand) cand[slot] = pack_cand(kv[e], 4 * i + e);
         }
     }
   }
@@ -271,16 +272,38 @@ __global__ void __launch_bounds__(256) topk_select2_kernel(const float* __restri
     }
   };
   if (ncand <= kTopkCand) {
-    // ---- 4. exact ranks by counting: (key, lower column first) is a strict order
-    for (int i = threadIdx.x; i < ncand; i += 256) {
-      const uint32_t ki = cand_key[i];
-      const int ci = cand_col[i];
-      int rank = 0;
-      for (int j = 0; j < ncand; ++j) {
-        const uint32_t kj = cand_key[j];
-        rank += (kj > ki || (kj == ki && cand_col[j] < ci)) ? 1 : 0;
+    // ---- 4. exact ranks by counting: rank = candidates above this one; rank < k <=> selected, and rank is its slot.
+    // The ncand^2 comparisons are the bulk of this kernel's instructions (ncu source view, profiles/r02p_*): one 64-bit
+    // broadcast load and compare per pair, and every candidate's count is split over `parts` threads so that all 256
+    // threads count (typically ncand = 2-3 k < 256).
+    const int parts = ncand >= kTopkCand ? 1 : min(8, (kTopkCand + ncand - 1) / max(ncand, 1));
+    if (parts == 1) {
+      for (int i = threadIdx.x; i < ncand; i += 256) {
+        const unsigned long long ci = cand[i];
+        int rank = 0;
+#pragma unroll 8
+        for (int j = 0; j < ncand; ++j) rank += cand[j] > ci ? 1 : 0;
+        if (rank < k) emit(rank, cand_col_of(ci), cand_key_of(ci));
       }
-      if (rank < k) emit(rank, ci, ki);
+    } else {
+      for (int i = threadIdx.x; i < ncand; i += 256) cand_rank[i] = 0;
+      __syncthreads();
+      const int seg = (ncand + parts - 1) / parts;
+      for (int w = threadIdx.x; w < ncand * parts; w += 256) {
+        const int part = w / ncand, i = w - part * ncand;
+        const int j0 = part * seg, j1 = min(ncand, j0 + seg);
+        const unsigned long long ci = cand[i];
+        int cntp = 0;
+#pragma unroll 8
+        for (int j = j0; j < j1; ++j) cntp += cand[j] > ci ? 1 : 0;
+        atomicAdd(&cand_rank[i], cntp);
+      }
+      __syncthreads();
+      for (int i = threadIdx.x; i < ncand; i += 256) {
+        const int rank = cand_rank[i];
+        const unsigned long long ci = cand[i];
+        if (rank < k) emit(rank, cand_col_of(ci), cand_key_of(ci));
+      }
     }
   } else {
     // ---- 4'. exact 4-pass 8-bit radix select over the keys >= bound, then an ordered compaction (column order)

@@ -357,6 +357,8 @@ def test_config2_shape_properties():
     ("topk", 1, 256, 32768, 128),     # rows too long for the candidate list in shared memory (keys-only select)
     ("tied", 1, 2048, 32768, 256),    # config 5: Pythia-1.4b MLP-out, dict_ratio 16
     ("untied", 2, 768, 3072, 384),    # untied at GPT-2 width
+    ("tied", 1, 4096, 8192, 256),     # Pythia-6.9b residual width (row kernels with 8 float4 per thread)
+    ("untied", 1, 5120, 1024, 128),   # Pythia-12b width: not a power of two, 16 float4 per thread
 ])
 def test_other_config_shapes(shape):
     """Forward quantities (x̂, loss) on a row slice and one optimiser step at the widths of BASELINE configs 3/5."""
@@ -408,6 +410,50 @@ def test_other_config_shapes(shape):
     for _ in range(3):
         after, _ = ens.step_batch(X)
     assert bool((after["loss"] < before).all()) and all(torch.isfinite(v).all() for v in ens.params.values())
+
+
+@pytest.mark.parametrize("kind,d,n,B", [("tied", 4096, 1024, 192), ("untied", 5120, 512, 130)])
+def test_wide_activation_widths_backward(kind, d, n, B):
+    """d beyond BASELINE's 2048 (Pythia-6.9b / -12b residual widths): gradients against the fp64 oracle with the kink
+    pinned, then three steps against the fp32 reference step (the Adam / renormalise / re-split row kernels hold 8 and
+    16 float4 per thread at these widths)."""
+    import sparse_coding_b200 as S
+    torch.manual_seed(0)
+    gen = torch.Generator().manual_seed(7)
+    if kind == "tied":
+        models = [S.FunctionalTiedSAE.init(d, n, 1e-3)]
+        sig = S.FunctionalTiedSAE
+    else:
+        models = [S.FunctionalSAE.init(d, n, 1e-3, bias_decay=0.02)]
+        sig = S.FunctionalSAE
+    for p, _b in models:
+        p["encoder_bias"] = 0.05 * torch.randn(n, generator=gen)
+    clone = lambda ms: [({k: v.clone() for k, v in p.items()}, {k: v.clone() for k, v in b.items()}) for p, b in ms]
+    ens = S.FunctionalEnsemble(clone(models), sig, S.adam, {"lr": 1e-3}, device="cuda")
+    X = torch.randn(B, d, generator=gen)
+    grads, (loss, aux) = ens.grads_batch(X.cuda())
+    code = aux["c"].dense().cpu()
+    pd = {k: v.double() for k, v in models[0][0].items()}
+    alpha = float(models[0][1]["l1_alpha"])
+    if kind == "tied":
+        f0 = O.tied_forward(pd["encoder"], pd["encoder_bias"], X.double(), alpha)
+        active = torch.where(f0["Z"].abs() < kink_window(f0["Z"]), code[0] > 0, f0["Z"] > 0)
+        f = O.tied_grads(pd["encoder"], pd["encoder_bias"], X.double(), alpha, 0.0, None, active=active)
+    else:
+        bd = float(models[0][1]["bias_decay"])
+        f0 = O.untied_forward(pd["encoder"], pd["encoder_bias"], pd["decoder"], X.double(), alpha, bd)
+        active = torch.where(f0["Z"].abs() < kink_window(f0["Z"]), code[0] > 0, f0["Z"] > 0)
+        f = O.untied_grads(pd["encoder"], pd["encoder_bias"], pd["decoder"], X.double(), alpha, bd, active=active)
+    assert abs(float(loss["loss"][0]) - float(f0["loss"])) <= REL * float(f0["loss"])
+    for k, g in f["grads"].items():
+        assert relnorm(grads[k][0], g) <= 2e-4, (kind, k, relnorm(grads[k][0], g))
+    ref = O.RefPortEnsemble(clone(models), O.SIG_LOSSES[kind], lr=1e-3)
+    for _ in range(3):
+        le, _ = ens.step_batch(X.cuda())
+        lr_, _ = ref.step_batch(X)
+    assert abs(float(le["loss"][0]) - float(lr_["loss"][0])) <= 1e-3 * float(lr_["loss"][0])
+    for k in ens.params:
+        assert relnorm(ens.params[k][0], ref.params[k][0]) <= 2e-3, (kind, k)
 
 
 @pytest.mark.parametrize("bwd_passes", [3, 1])
