@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define SCE_VERSION 200 /* major*10000 + minor*100 + patch */
+#define SCE_VERSION 201 /* major*10000 + minor*100 + patch */
 
 typedef enum sce_status {
   SCE_OK = 0,
@@ -72,6 +72,10 @@ typedef struct sce_desc {
   int arith;            /* enum sce_arith; 0 = AUTO */
   int topk_k_max;       /* SCE_TOPK: the largest buffers["sparsity"] of the ensemble (1..256) enables the k-sparse decode /
                            code-gradient kernels; 0 = unknown: dense GEMMs on the k-sparse code, as the reference does */
+  int centering;        /* FunctionalTiedSAE.center (sae_ensemble.py:126-128) applied to the batch on the device:
+                           x_c[m] = (rot[m] (x - trans[m])) * scale[m]. 0 = off (identity centring); 1 = the batch is one
+                           [B,d] array shared by all models; 2 = [M,B,d]. Needs x_per_model = 1 (the centred batch differs per
+                           model) and the three center_* buffers. */
 } sce_desc;
 
 /* Device pointers owned by the caller; all fp32 unless noted. Unused ones are NULL. */
@@ -91,6 +95,9 @@ typedef struct sce_buffers {
   const long long* sparsity;      /* [M]   buffers["sparsity"] (topk k) or NULL */
   void* workspace;                /* >= sce_workspace_bytes(desc), 1024-byte aligned */
   size_t workspace_bytes;
+  const float* center_trans;      /* [M,d]   buffers["center_trans"]  (desc.centering != 0; else NULL) */
+  const float* center_rot;        /* [M,d,d] buffers["center_rot"]    */
+  const float* center_scale;      /* [M,d]   buffers["center_scale"]  */
 } sce_buffers;
 
 typedef struct sce_plan sce_plan;

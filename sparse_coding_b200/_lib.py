@@ -35,7 +35,7 @@ class SceDesc(C.Structure):
         ("x_per_model", C.c_int),
         ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float), ("eps_root", C.c_float),
         ("adam_count_mode", C.c_int), ("fwd_passes", C.c_int), ("bwd_passes", C.c_int), ("norm_floor", C.c_float),
-        ("arith", C.c_int), ("topk_k_max", C.c_int),
+        ("arith", C.c_int), ("topk_k_max", C.c_int), ("centering", C.c_int),
     ]
 
 
@@ -46,6 +46,7 @@ class SceBuffers(C.Structure):
         ("decoder_m", C.c_void_p), ("decoder_v", C.c_void_p),
         ("l1_alpha", C.c_void_p), ("bias_decay", C.c_void_p), ("coef_mask", C.c_void_p), ("sparsity", C.c_void_p),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+        ("center_trans", C.c_void_p), ("center_rot", C.c_void_p), ("center_scale", C.c_void_p),
     ]
 
 

@@ -53,6 +53,7 @@ struct GemmMaps {  // tensor maps of one GEMM for one batch size (x8: third plan
 };
 struct BatchMaps {
   GemmMaps encode, decode, dcode, dw_enc, dw_dec;
+  GemmMaps center;             // centring: A = (x - trans) planes [M,B,d], B = rot planes [M,d,d], both K-major
   CUtensorMap st_c_hi, st_c_lo, st_c_x8, st_dz_hi, st_dz_lo, st_dz_x8;  // epilogue TMA-store maps
   CUtensorMap st_scores;                                                // top-k: fp32 scores
   cudaGraphExec_t graph;       // captured step for this batch size (launch-bound shapes), or nullptr
@@ -76,6 +77,9 @@ struct sce_plan {
   __nv_bfloat16 *g_hi, *g_lo;     // [M, Bmax, d]
   __nv_bfloat16 *dz_hi, *dz_lo;   // [M, Bmax, n]   (top-k: fp32 scores alias these planes)
   uint8_t *x_x8, *wenc_x8, *wdec_x8, *c_x8, *g_x8, *dz_x8;
+  __nv_bfloat16 *rot_hi, *rot_lo;  // centring: operand planes of buffers["center_rot"] [M, d, d]
+  uint8_t* rot_x8;
+  float* x_centered;              // centring: the centred batch [M, B, d] (B, not Bmax, rows per model: what a caller's [M,B,d] looks like)
   float* scores;                  // top-k: fp32 scores [M, Bmax, n] of the encode GEMM
   uint32_t* tk_cmax;              // top-k: largest key per 32-column chunk of the scores [M, Bmax, n_chunks] (EpiScoresTma)
   int topk_cmax;                  // 1: the selection works from the chunk maxima (SCE_TOPK_CMAX=0 turns it off)
@@ -136,6 +140,8 @@ static int validate(const sce_desc* d) {
   if (d->d > 8192) return fail(SCE_ERR_INVALID, "d = %d > 8192 is not supported by the row kernels", d->d);
   if ((d->fwd_passes != 1 && d->fwd_passes != 3) || (d->bwd_passes != 1 && d->bwd_passes != 3))
     return fail(SCE_ERR_INVALID, "fwd_passes / bwd_passes must be 1 or 3");
+  if (d->centering < 0 || d->centering > 2) return fail(SCE_ERR_INVALID, "centering must be 0, 1 or 2");
+  if (d->centering && !d->x_per_model) return fail(SCE_ERR_INVALID, "centering needs x_per_model = 1 (the centred batch differs per model)");
   if (d->arith < SCE_ARITH_AUTO || d->arith > SCE_ARITH_F16F8) return fail(SCE_ERR_INVALID, "unknown arith %d", d->arith);
   if (d->arith == SCE_ARITH_F16F8 && (d->d % 16 || d->n % 16))
     return fail(SCE_ERR_INVALID, "arith = F16F8 needs d (%d) and n (%d) to be multiples of 16 (TMA pitch of the 8-bit planes)",
@@ -243,6 +249,13 @@ static size_t carve(sce_plan* p, const sce_desc& d, uint8_t* base) {
       wnf = c.take<float>(M * n * dd);
     }
   }
+  __nv_bfloat16 *roth = nullptr, *rotl = nullptr;
+  uint8_t* rot8 = nullptr;
+  float* xcen = nullptr;
+  if (d.centering) {
+    planes(M * dd * dd, roth, rotl, rot8);
+    xcen = c.take<float>(M * B * dd);
+  }
   auto rf = c.take<uint32_t>(kFlagWords);   // [0] residual flag, [kAbsmaxWord] input range monitor, [kBadWord] health (separate 128-byte lines)
   if (p) {
     p->x_stage = X;
@@ -274,6 +287,10 @@ static size_t carve(sce_plan* p, const sce_desc& d, uint8_t* base) {
     p->loss_stage = ls;
     p->nnz_stage = ns;
     p->res_flags = rf;
+    p->rot_hi = roth;
+    p->rot_lo = rotl;
+    p->rot_x8 = rot8;
+    p->x_centered = xcen;
     p->scores = sc;
     p->tk_cmax = tcm;
     p->tk_col = tkc;
@@ -385,6 +402,16 @@ static int build_maps(sce_plan* p, int B, BatchMaps** out) {
   // encode: A = x [xm,B,d] K-major, B = Wenc [M,n,d] K-major
   ok &= actk(m->encode, 0, X, xm, dd, bk_enc);
   ok &= dict_b(m->encode, WE, bn_for(d.n) / (pair_ok(p->pair_encode, B, d.n) ? 2 : 1), bk_enc);
+  if (d.centering) {
+    // centring: A = (x - trans) planes in the X planes (the encode A maps), B = rot [M,d,d] K-major, output d columns
+    for (int t = 0; t < 1; ++t) {
+      m->center.a_hi[t] = m->encode.a_hi[t];
+      m->center.a_lo[t] = m->encode.a_lo[t];
+      m->center.a_x8[t] = m->encode.a_x8[t];
+    }
+    ok &= operand_maps(ar, &m->center.b_hi[0], &m->center.b_lo[0], &m->center.b_x8[0], p->rot_hi, p->rot_lo, p->rot_x8, M, dd, dd,
+                       dd * dd, bn_for(d.d) / (pair_ok(p->pair_encode, B, d.d) ? 2 : 1), bk_enc);
+  }
   // decode: A = c [M,B,n] K-major, B = Wdec [M,n,d] MN-major (bk k-rows per box)
   ok &= actk(m->decode, 0, C, M, n, bk_dec);
   ok &= dict_b(m->decode, WD, bk_dec, 0);
@@ -611,6 +638,27 @@ static int run_pipeline_t(sce_plan* p, const float* x, int B, float* x_hat, bool
   const int tiles_mB = (B + kBM - 1) / kBM;
 
   prof_mark(p, SCE_PHASE_SPLIT, st);
+  // the f16f8 kernels run narrow outputs on single CTAs (build_maps)
+  auto pair_ok = [&](int flag, int rows, int out_cols) { return use_pair(flag, rows) && !(f8 && out_cols <= 128); };
+  if (d.centering) {
+    // ---- centring (sae_ensemble.py:126-128): (x - trans[m]) -> planes, GEMM with rot[m] (all split passes), * scale[m]
+    // -> the per-model fp32 batch every kernel below reads as `x`
+    const long long n4 = (long long)B * dd / 4;
+    const int blocks = (int)((n4 + 255) / 256 < 1024 ? (n4 + 255) / 256 : 1024);
+    center_split_kernel<AR><<<dim3(blocks, M), 256, 0, st>>>(
+        x, d.centering == 2 ? (long long)B * dd : 0, p->b.center_trans, p->x_hi, p->x_lo, p->x_x8, Bm * dd, B, dd);
+    CUDA_TRY(cudaGetLastError());
+    EpiCenter::Params cp;
+    cp.out = p->x_centered;
+    cp.model_stride = (long long)B * dd;
+    cp.ld = dd;
+    cp.col_scale = p->b.center_scale;
+    rc = launch_k<EpiCenter, false, false, AR>(dd > 128, p->bk_encode, pair_ok(p->pair_encode, B, dd), p, maps->center, 1, one, one,
+                                              dd, 3, B, dd, cp, st);
+    if (rc) return rc;
+    launches += 2;
+    x = p->x_centered;
+  }
   // ---- x -> (hi, lo): per model slabs are batch_max apart in the workspace
   if constexpr (f8) CUDA_TRY(cudaMemsetAsync(p->res_flags, 0, sizeof(uint32_t), st));
   for (int m = 0; m < p->xm; ++m) {
@@ -627,9 +675,6 @@ static int run_pipeline_t(sce_plan* p, const float* x, int B, float* x_hat, bool
   // alpha / B, or (f16f8, backward on r = g B d / 2) alpha d / 2
   l1_over_b_kernel<<<(M + 127) / 128, 128, 0, st>>>(p->b.l1_alpha, p->l1_over_b, M, f8 ? 0.5f * (float)dd : 1.0f / (float)B);
   ++launches;
-  // the f16f8 kernels run narrow outputs on single CTAs (build_maps)
-  auto pair_ok = [&](int flag, int rows, int out_cols) { return use_pair(flag, rows) && !(f8 && out_cols <= 128); };
-
   // the batch's residual-plane flag, for the GEMMs that read x as their A (encode) or B (weight gradient, set 0) operand
   ResFlags x_is_a, x_is_b;
   if constexpr (f8) {
@@ -784,7 +829,7 @@ static int run_pipeline_t(sce_plan* p, const float* x, int B, float* x_hat, bool
       const bool pair = pair_ok(p->pair_dw, n, dd);
       if constexpr (f8) {
         // d > 256: both 256-column halves of a dictionary row block from one A (dz / c) tile per K block (NSUB = 2)
-        if (dd > 256 && pair && p->dw_nsub2)
+        if (dd % 512 == 0 && pair && p->dw_nsub2)
           return launch_gemm_t<EpiStoreF32, 256, kBkF8, true, true, 4, false, true, kArithF16F8, 2>(p, gm, nsets, ab, bb, B, p->dw_passes, n, dd, sp, st, rf);
         if (dd > 128)
           return pair ? launch_gemm_t<EpiStoreF32, 256, kBkF8, true, true, 6, false, true, kArithF16F8>(p, gm, nsets, ab, bb, B, p->dw_passes, n, dd, sp, st, rf)
@@ -890,7 +935,7 @@ int sce_plan_create(const sce_desc* desc, const sce_buffers* buffers, sce_plan**
   // 256 x 512 weight-gradient tiles (one A tile for both column halves): DRAM traffic of the launch 5.69 -> 4.25 GB
   // at config 2, device time unchanged within the run-to-run noise (1.51 / 1.50 / 1.57 ms against 1.51 / 1.50 ms: the
   // kernel is bound by the power-limited tensor rate either way) — off by default, kept as a knob
-  p->dw_nsub2 = tune_flag("SCE_TUNE_DW_NSUB2", 0);
+  p->dw_nsub2 = tune_flag("SCE_TUNE_DW_NSUB2", 1);
   p->dw_collector = tune_flag("SCE_TUNE_DW_COLL", 1);
   p->bk_encode = tune_bk("SCE_TUNE_BK_ENCODE", 64);
   p->bk_decode = tune_bk("SCE_TUNE_BK_DECODE", 32);
@@ -955,6 +1000,17 @@ int sce_prepare(sce_plan* p, void* stream) {
     CUDA_TRY(cudaMemsetAsync(p->act_pos, 0, (size_t)d.n_models * ((d.n + 31) / 32) * d.batch_max * sizeof(uint32_t), st));
     CUDA_TRY(cudaMemsetAsync(p->tk_cnt, 0, (size_t)d.n_models * d.batch_max * sizeof(int), st));
   }
+  if (d.centering) {
+    if (!p->b.center_trans || !p->b.center_rot || !p->b.center_scale)
+      return fail(SCE_ERR_INVALID, "centering needs the center_trans / center_rot / center_scale buffers");
+    const long long n4 = (long long)d.n_models * d.d * d.d / 4;
+    const int blocks = (int)((n4 + 255) / 256 < 2048 ? (n4 + 255) / 256 : 2048);
+    if (p->arith == kArithF16F8)
+      split_rows_kernel<kArithF16F8><<<blocks, 256, 0, st>>>(p->b.center_rot, p->rot_hi, p->rot_lo, p->rot_x8, n4, nullptr);
+    else
+      split_rows_kernel<kArithBf16x3><<<blocks, 256, 0, st>>>(p->b.center_rot, p->rot_hi, p->rot_lo, nullptr, n4, nullptr);
+    CUDA_TRY(cudaGetLastError());
+  }
   AdamHyper h = hyper_for(p, 1);
   int rc;
   if (d.variant == SCE_UNTIED) {
@@ -971,6 +1027,9 @@ int sce_forward(sce_plan* p, const float* x, int B, float* x_hat, float* out_los
   if (!p) return fail(SCE_ERR_INVALID, "plan is NULL");
   return run_pipeline(p, x, B, x_hat, false, out_losses, out_nnz, static_cast<cudaStream_t>(stream));
 }
+
+// models' worth of rows in the caller's batch: 1 when it is shared ([B,d]; also with centering = 1), else M
+static int input_models(const sce_plan* p) { return p->d.centering == 1 ? 1 : p->xm; }
 
 // every launch of one optimisation step, in order, on `st` (also what gets captured into a CUDA graph)
 static int step_launches(sce_plan* p, const float* x, int B, float* out_losses, float* out_nnz, long long t,
@@ -1032,7 +1091,7 @@ int sce_step(sce_plan* p, const float* x, int B, float* out_losses, float* out_n
     BatchMaps* maps = nullptr;
     rc = build_maps(p, B, &maps);
     if (rc) return rc;
-    const size_t bytes = (size_t)p->xm * B * p->d.d * sizeof(float);
+    const size_t bytes = (size_t)input_models(p) * B * p->d.d * sizeof(float);
     if (x != p->x_stage) CUDA_TRY(cudaMemcpyAsync(p->x_stage, x, bytes, cudaMemcpyDeviceToDevice, st));
     // the captured kernels write the plan's own staging outputs (stable addresses: callers may pass fresh tensors
     // every step, as the reference returns them); the results are copied out below
@@ -1120,7 +1179,7 @@ int sce_step_host(sce_plan* p, const float* x_host, int B, float* out_losses_hos
   if (!x_host) return fail(SCE_ERR_INVALID, "x_host is NULL");
   if (B < 1 || B > p->d.batch_max) return fail(SCE_ERR_INVALID, "B = %d outside [1, batch_max = %d]", B, p->d.batch_max);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const size_t bytes = (size_t)p->xm * B * p->d.d * sizeof(float);
+  const size_t bytes = (size_t)input_models(p) * B * p->d.d * sizeof(float);
   CUDA_TRY(cudaMemcpyAsync(p->x_stage, x_host, bytes, cudaMemcpyHostToDevice, st));
   int rc = sce_step(p, p->x_stage, B, p->loss_stage, p->nnz_stage, st);
   if (rc) return rc;

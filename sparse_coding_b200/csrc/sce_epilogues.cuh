@@ -476,6 +476,41 @@ struct EpiScoresTma {
   }
 };
 
+// ------------------------------------------------------------------------------------------------
+// centring GEMM (FunctionalTiedSAE.center, sae_ensemble.py:126-128): acc = rot (x - trans); out = acc * scale[col], fp32
+// [M][B][d] — the per-model batch every later kernel of the step reads (split into operand planes by split_rows_kernel,
+// subtracted from x^ by the decode epilogue).
+// ------------------------------------------------------------------------------------------------
+struct EpiCenter {
+  static constexpr int kCols = 32;
+  static constexpr int kWarpStageBytes = 0;
+  struct Params {
+    float* out;                // [M][B][ld]
+    long long model_stride;    // elements between models of `out`
+    int ld;
+    const float* col_scale;    // [M][ld]
+  };
+  const Params& P;
+  const TileCoord& T;
+  int m_total, n_total;
+  __device__ EpiCenter(const Params& p, const TileCoord& t, int m, int n, uint8_t*) : P(p), T(t), m_total(m), n_total(n) {}
+  __device__ __forceinline__ void chunk(int c, const uint32_t (&r)[32]) {
+    if (T.row >= m_total) return;
+    const int col = T.col0 + c;
+    float* o = P.out + (long long)T.model * P.model_stride + (long long)T.row * P.ld + col;
+    const float* sc = P.col_scale + (long long)T.model * P.ld + col;
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      if (col + j < n_total) {   // n_total % 4 == 0
+        const float4 s4 = __ldg(reinterpret_cast<const float4*>(sc + j));
+        *reinterpret_cast<float4*>(o + j) = make_float4(__uint_as_float(r[j]) * s4.x, __uint_as_float(r[j + 1]) * s4.y,
+                                                        __uint_as_float(r[j + 2]) * s4.z, __uint_as_float(r[j + 3]) * s4.w);
+      }
+    }
+  }
+  __device__ __forceinline__ void finish() {}
+};
+
 using EpiEncode = EpiEncodeT<kArithBf16x3>;
 using EpiDecode = EpiDecodeT<kArithBf16x3>;
 using EpiDcode = EpiDcodeT<kArithBf16x3>;

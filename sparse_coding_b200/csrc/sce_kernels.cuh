@@ -84,6 +84,28 @@ __global__ void split_rows_kernel(const float* __restrict__ x, void* __restrict_
 }
 
 // ------------------------------------------------------------------------------------------------
+// centring, first half: (x - trans[m]) -> operand planes of model m (the A operand of the rotation GEMM, EpiCenter).
+// x: [B][d] shared by the models (x_model_stride = 0) or [M][B][d]; planes of model m start at m * plane_model_stride.
+// ------------------------------------------------------------------------------------------------
+template <int ARITH>
+__global__ void center_split_kernel(const float* __restrict__ x, long long x_model_stride, const float* __restrict__ trans,
+                                    void* __restrict__ hi, void* __restrict__ lo, void* __restrict__ x8,
+                                    long long plane_model_stride, int B, int d) {
+  const int model = blockIdx.y;
+  const int d4 = d >> 2;
+  const long long n4 = (long long)B * d4;
+  const float4* xs = reinterpret_cast<const float4*>(x + (long long)model * x_model_stride);
+  const float4* ts = reinterpret_cast<const float4*>(trans + (long long)model * d);
+  const long long p4 = (long long)model * plane_model_stride / 4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = xs[i];
+    const float4 t = __ldg(ts + (int)(i % d4));
+    const float vv[4] = {v.x - t.x, v.y - t.y, v.z - t.z, v.w - t.w};
+    store_planes4<ARITH>(vv, hi, lo, x8, p4 + i);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // chunk row gather (+ fp16 -> fp32, + mean-centring): out[r,:] = float(chunk[idx[r],:]) - sub
 // one warp per row; big_sweep.py:168 and :359-364
 // ------------------------------------------------------------------------------------------------

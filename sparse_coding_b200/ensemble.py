@@ -238,7 +238,7 @@ class FunctionalEnsemble:
         return not (bool((b["center_rot"] == eye).all()) and bool((b["center_trans"] == 0).all())
                     and bool((b["center_scale"] == 1).all()))
 
-    def _build_plan(self, batch_max: int, x_per_model: bool):
+    def _build_plan(self, batch_max: int, x_per_model: bool, centering: int = 0):
         dev = self._require_cuda()
         lib = _lib.load()
         for k, v in self.params.items():
@@ -256,7 +256,8 @@ class FunctionalEnsemble:
             fwd_passes=self.fwd_passes, bwd_passes=self.bwd_passes,
             norm_floor=0.0 if self._variant == "topk" else 1e-8,
             arith=_lib.ARITH_CODE[getattr(self, "_arith_fallback", None) or getattr(self, "arith", "auto")],
-            topk_k_max=int(self.buffers["sparsity"].max()) if self._variant == "topk" else 0)
+            topk_k_max=int(self.buffers["sparsity"].max()) if self._variant == "topk" else 0,
+            centering=centering)
         nbytes = lib.sce_workspace_bytes(C.byref(desc))
         if nbytes == 0:
             _lib.check(-1, "sce_workspace_bytes")
@@ -293,13 +294,19 @@ class FunctionalEnsemble:
         if self._variant == "topk":
             eb["sparsity"] = self.buffers["sparsity"].to(device=dev, dtype=torch.int64).contiguous()
             bufs.sparsity = eb["sparsity"].data_ptr()
+        if centering:
+            # FunctionalTiedSAE.center (sae_ensemble.py:126-128) runs on the device: (x - trans) planes, GEMM with rot, * scale
+            for name in ("center_trans", "center_rot", "center_scale"):
+                eb[name] = self.buffers[name].to(device=dev, dtype=torch.float32).contiguous()
+            bufs.center_trans, bufs.center_rot, bufs.center_scale = (eb["center_trans"].data_ptr(), eb["center_rot"].data_ptr(),
+                                                                     eb["center_scale"].data_ptr())
         bufs.workspace, bufs.workspace_bytes = ws_ptr, nbytes
         plan = C.c_void_p()
         with torch.cuda.device(dev):
             _lib.check(lib.sce_plan_create(C.byref(desc), C.byref(bufs), C.byref(plan)), "sce_plan_create")
             self._plan = plan
             self._engine_buffers = eb
-            self._plan_key = (batch_max, bool(x_per_model))
+            self._plan_key = (batch_max, bool(x_per_model), int(centering))
             _lib.check(lib.sce_set_step_count(plan, self._steps), "sce_set_step_count")
             _lib.check(lib.sce_prepare(plan, self._stream()), "sce_prepare")
         self._plan_steps = 0
@@ -335,18 +342,17 @@ class FunctionalEnsemble:
         if x.dtype != torch.float32:
             x = x.float()
         per_model = not expand_dims
-        if self._needs_centering():
-            xe = x.expand(self.n_models, *x.shape) if expand_dims else x
-            b = self.buffers
-            x = torch.bmm(xe - b["center_trans"][:, None, :], b["center_rot"].transpose(1, 2)) * b["center_scale"][:, None, :]
-            per_model = True
+        # non-identity centring (sae_ensemble.py:126-128) is applied by the engine (sce_desc.centering): 1 = this batch is
+        # one [B,d] array for all models, 2 = [M,B,d]; the centred batch is per model either way
+        centering = (1 if expand_dims else 2) if self._needs_centering() else 0
         x = x.contiguous()
         B = x.shape[-2]
-        if x.shape[-1] != self._d or (per_model and x.shape[0] != self.n_models):
+        if x.shape[-1] != self._d or (per_model and (x.dim() != 3 or x.shape[0] != self.n_models)):
             raise ValueError(f"batch shape {tuple(x.shape)} does not match ensemble (M={self.n_models}, d={self._d})")
+        plan_per_model = per_model or centering != 0
         key = self._plan_key
-        if self._plan is None or key is None or key[1] != per_model or B > key[0]:
-            self._build_plan(max(B, key[0]) if key else B, per_model)
+        if self._plan is None or key is None or key[1] != plan_per_model or key[2] != centering or B > key[0]:
+            self._build_plan(max(B, key[0]) if key else B, plan_per_model, centering)
         return x, B
 
     def _losses_dict(self) -> Dict[str, Tensor]:
@@ -426,7 +432,7 @@ class FunctionalEnsemble:
         if resolved == "f16f8" and getattr(self, "arith", "auto") == "auto":
             self._arith_fallback = "bf16x3"
             key = self._plan_key
-            self._build_plan(key[0], key[1])
+            self._build_plan(key[0], key[1], key[2])
             warnings.warn(
                 f"a batch left the range of the f16f8 operand arithmetic (largest |activation| {amax:g}; fp16 holds "
                 "|v| < 65504) or produced a non-finite loss: the affected updates were skipped on the device, the "

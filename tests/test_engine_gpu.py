@@ -130,6 +130,46 @@ def test_golden_reconstruction(golden, name, arith):
 
 
 @pytest.mark.parametrize("arith", ARITHS)
+@pytest.mark.parametrize("per_model", [False, True])
+def test_device_side_centring(arith, per_model):
+    """FunctionalTiedSAE.center (sae_ensemble.py:126-128) on the device — (x - trans) planes, rotation GEMM, scale — at a
+    realistic width, for a batch shared by the models and for per-model batches (expand_dims=False): losses, centred
+    reconstruction and gradients against the fp64 oracle on the fp64-centred batch, then three steps against the fp32
+    reference step."""
+    import sparse_coding_b200 as S
+    M, d, n, B = 3, 512, 1024, 300
+    gen = torch.Generator().manual_seed(11)
+    torch.manual_seed(5)
+    models = []
+    for i in range(M):
+        q, _ = torch.linalg.qr(torch.randn(d, d, generator=gen))
+        p, b = S.FunctionalTiedSAE.init(d, n, 10 ** (-3 + 0.5 * i), translation=0.3 * torch.randn(d, generator=gen),
+                                        rotation=q.contiguous(), scaling=0.5 + torch.rand(d, generator=gen))
+        p["encoder_bias"] = 0.05 * torch.randn(n, generator=gen)
+        models.append((p, b))
+    clone = lambda ms: [({k: v.clone() for k, v in p.items()}, {k: v.clone() for k, v in b.items()}) for p, b in ms]
+    ens = S.FunctionalEnsemble(clone(models), S.FunctionalTiedSAE, S.adam, {"lr": 1e-3}, device="cuda", arith=arith)
+    X = torch.randn(M, B, d, generator=gen) if per_model else torch.randn(B, d, generator=gen)
+    kw = dict(expand_dims=not per_model)
+    grads, (loss, aux) = ens.grads_batch(X.cuda(), **kw)
+    code = aux["c"].dense().cpu()
+    _, _, x_hat = ens.forward_batch(X.cuda(), return_x_hat=True, **kw)
+    for i, (p, b) in enumerate(models):
+        Xi = X[i] if per_model else X
+        f, f0 = tied_grads_engine_kinks(p, b, Xi, code[i])
+        assert relnorm(x_hat[i], f0["x_hat"]) <= REL, (i, relnorm(x_hat[i], f0["x_hat"]))
+        assert abs(float(loss["loss"][i]) - float(f0["loss"])) <= REL * float(f0["loss"])
+        for k in ("encoder", "encoder_bias"):
+            assert relnorm(grads[k][i], f["grads"][k]) <= 2e-4, (i, k, relnorm(grads[k][i], f["grads"][k]))
+    ref = O.RefPortEnsemble(clone(models), O.SIG_LOSSES["tied"], lr=1e-3)
+    for _ in range(3):
+        le, _ = ens.step_batch(X.cuda(), **kw)
+        lr_, _ = ref.step_batch(X, **kw)
+    assert torch.allclose(le["loss"].cpu(), lr_["loss"], rtol=1e-3)
+    assert relnorm(ens.params["encoder"], ref.params["encoder"]) <= 2e-3
+
+
+@pytest.mark.parametrize("arith", ARITHS)
 def test_cfg1_golden(golden, arith):
     """BASELINE config 1 (d=128, n=256, B=1024, L1=1e-3): losses, per-row nnz and gradients of the reference."""
     fx = golden("cfg1")

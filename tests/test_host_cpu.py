@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     lib = _lib.load()
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.sce_version() == 200
+    assert lib.sce_version() == 201
 
 
 def test_abi_validation_without_device():
