@@ -430,10 +430,17 @@ static int build_maps(sce_plan* p, int B, BatchMaps** out) {
     ok &= act_a(m->dw_enc, 1, C, M, n);
     ok &= act_b(m->dw_enc, 1, G, M, dd);
   }
-  ok &= make_tmap_bf16_store32(&m->st_c_hi, p->c_hi, M, (uint64_t)B, n, Bm * n);
-  ok &= make_tmap_bf16_store32(&m->st_dz_hi, p->dz_hi, M, (uint64_t)B, n, Bm * n);
+  if (f8 && SCE_EPI_PAIR) {
+    // two adjacent chunks per bulk store (stage_pair_and_store): boxes of 64 columns x 32 rows, 128-byte rows
+    ok &= make_tmap_bf16_box(&m->st_c_hi, p->c_hi, M, (uint64_t)B, n, n, Bm * n, 64, 32, CU_TENSOR_MAP_SWIZZLE_128B);
+    ok &= make_tmap_bf16_box(&m->st_dz_hi, p->dz_hi, M, (uint64_t)B, n, n, Bm * n, 64, 32, CU_TENSOR_MAP_SWIZZLE_128B);
+  } else {
+    ok &= make_tmap_bf16_store32(&m->st_c_hi, p->c_hi, M, (uint64_t)B, n, Bm * n);
+    ok &= make_tmap_bf16_store32(&m->st_dz_hi, p->dz_hi, M, (uint64_t)B, n, Bm * n);
+  }
   if (f8) {
     auto st8 = [&](CUtensorMap* t, const void* base) {
+      if (SCE_EPI_PAIR) return make_tmap_u8_box(t, base, M, (uint64_t)B, n, n, Bm * n, 64, 32, CU_TENSOR_MAP_SWIZZLE_64B);
       return make_tmap_u8_box(t, base, M, (uint64_t)B, n, n, Bm * n, 32, 32, CU_TENSOR_MAP_SWIZZLE_32B);
     };
     ok &= st8(&m->st_c_lo, p->c_lo) && st8(&m->st_c_x8, p->c_x8) && st8(&m->st_dz_lo, p->dz_lo) && st8(&m->st_dz_x8, p->dz_x8);
@@ -537,10 +544,12 @@ static int launch_gemm_t(const sce_plan* p, const GemmMaps& maps, int nsets, con
 template <class Epi, bool B_MN, bool SPLIT, int ARITH, class... Args>
 static int launch_k(bool wide, int bk, bool pair, Args&&... a) {
   if constexpr (ARITH == kArithF16F8) {
+    // epilogues that stage two chunks per bulk store take 8 KB per epilogue warp: one ring stage less
+    constexpr int big = Epi::kWarpStageBytes > 4096 ? 1 : 0;
     if (wide)
-      return pair ? launch_gemm_t<Epi, 256, kBkF8, false, B_MN, 6, false, true, kArithF16F8>(a...)
-                  : launch_gemm_t<Epi, 256, kBkF8, false, B_MN, 4, false, false, kArithF16F8>(a...);
-    return launch_gemm_t<Epi, 128, kBkF8, false, B_MN, 6, false, false, kArithF16F8>(a...);
+      return pair ? launch_gemm_t<Epi, 256, kBkF8, false, B_MN, 6 - big, false, true, kArithF16F8>(a...)
+                  : launch_gemm_t<Epi, 256, kBkF8, false, B_MN, 4 - big, false, false, kArithF16F8>(a...);
+    return launch_gemm_t<Epi, 128, kBkF8, false, B_MN, 6 - big, false, false, kArithF16F8>(a...);
   } else {
   if (wide) {
     if (bk == 32)

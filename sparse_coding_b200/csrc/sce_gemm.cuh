@@ -18,6 +18,7 @@
 // warp per scheduler is latency-bound: the r01a profile showed ~37 issued instructions per element
 // at IPC ~0.25 holding the tensor pipe at 31 % in the encode GEMM.
 #pragma once
+#include <type_traits>
 #include "sce_ptx.cuh"
 
 namespace sce {
@@ -100,6 +101,12 @@ struct GemmSmem {
 // accumulator by 2^-kLoShift. One accumulator, so the double-buffered TMEM stages stay, and the chain of dominant
 // products is as short as with SPLIT_ACC.
 constexpr int kArithBf16x3 = 0, kArithF16F8 = 1;
+
+// epilogues may declare `static constexpr bool kPairChunks = true` (see the epilogue loop of gemm_split_kernel)
+template <class Epi, class = void>
+struct epi_pairs_chunks : std::false_type {};
+template <class Epi>
+struct epi_pairs_chunks<Epi, std::void_t<decltype(Epi::kPairChunks)>> : std::bool_constant<Epi::kPairChunks> {};
 
 //
 // NSUB = 2 (f16f8 only): the output tile is 256 x (2 * BN): both BN-column halves are accumulated from ONE A tile per
@@ -552,8 +559,13 @@ gemm_split_kernel(const __grid_constant__ GemmParams<typename Epi::Params> p) {
       const uint32_t taddr = tmem_base + uint32_t((acc * NSUB + sub) * BN) + (uint32_t(wq * 32) << 16);
       constexpr int kChunks = BN / EC;
       static_assert(kChunks % 2 == 0, "the two epilogue warp groups alternate chunks");
+      // chunk order of an epilogue warp group: alternating chunks (grp, grp + 2, ...) or, for epilogues that stage two
+      // adjacent chunks per bulk store (Epi::kPairChunks), alternating PAIRS: (2 grp, 2 grp + 1), (2 grp + 4, 2 grp + 5), ...
+      constexpr bool kPairs = epi_pairs_chunks<Epi>::value;
+      static_assert(!kPairs || (EC == 32 && kChunks % 4 == 0), "paired chunks: 32-column chunks, whole pairs per group");
 #pragma unroll 1
-      for (int c = grp; c < kChunks; c += 2) {
+      for (int it = 0; it < kChunks / 2; ++it) {
+        const int c = kPairs ? ((it >> 1) * 4 + 2 * grp + (it & 1)) : (grp + 2 * it);
         uint32_t r[EC];
         tmem_ld32(taddr + uint32_t(c * EC), *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
         if constexpr (EC == 64) tmem_ld32(taddr + uint32_t(c * EC + 32), *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
@@ -568,7 +580,7 @@ gemm_split_kernel(const __grid_constant__ GemmParams<typename Epi::Params> p) {
           }
         }
         tmem_ld_wait();
-        if (c + 2 >= kChunks && sub == nsub - 1) {
+        if (it == kChunks / 2 - 1 && sub == nsub - 1) {
           // all TMEM reads of this accumulator are done: hand it back to the MMA warp early
           tc_fence_before();
           __syncwarp();
