@@ -13,7 +13,10 @@
 #include "sce_gemm.cuh"
 
 #ifndef SCE_EPI_PAIR
-#define SCE_EPI_PAIR 1   // f16f8 encode / dcode epilogues: two adjacent chunks per bulk store (0: one chunk per store)
+// f16f8 encode / dcode epilogues: 1 = two adjacent chunks per bulk store (stage_pair_and_store), 0 = one chunk per store.
+// Measured slower (ncu, same box: encode 0.905 vs 0.841 ms, dcode 0.981 vs 0.954 ms; profiles/r02b_epilogue_writeout_experiments.txt):
+// kept as a build option only.
+#define SCE_EPI_PAIR 0
 #endif
 
 namespace sce {
