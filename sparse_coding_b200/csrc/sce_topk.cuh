@@ -94,6 +94,11 @@ struct TopkLists {
 //      (more candidates than the list holds — k > 256, many equal scores — : 4-pass radix select re-reading the row
 //      each pass, then an ordered compaction, as the first version of this kernel did for every row from shared memory)
 //   5. scatter the k entries into the zeroed planes, activity-mask bits, (column, value) list, per-row partials
+// With the chunk maxima of the scores epilogue (`cmax`: the largest key of every 32-column chunk of the row, written by
+// EpiScoresTma) steps 1 and 3 do not read the row: the thread maxima of step 1 are taken over the chunk maxima (chunk i
+// belongs to thread i % 256; the bound of step 2 then uses the warps whose 32 lanes all own a chunk), and step 3 lists the
+// chunks whose maximum reaches the bound and reads only those, a warp per 128-byte chunk. Rows with fewer than 32 chunks,
+// or with k beyond 32 per such warp, take the two full passes.
 // ------------------------------------------------------------------------------------------------
 constexpr int kTopkCand = 1024;
 __device__ __forceinline__ unsigned long long pack_cand(uint32_t key, int col) {
