@@ -16,6 +16,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <vector>
 #include <new>
 
 #include "../../include/sce.h"
@@ -81,6 +82,8 @@ struct sce_plan {
   uint8_t* rot_x8;
   float* x_centered;              // centring: the centred batch [M, B, d] (B, not Bmax, rows per model: what a caller's [M,B,d] looks like)
   float* scores;                  // top-k: fp32 scores [M, Bmax, n] of the encode GEMM
+  int* tk_models;                 // top-k gather kernel: the models sorted into k classes (device copy of tk_group_models)
+  int tk_groups, tk_group_off[5], tk_group_krows[4];   // classes: models [off[g], off[g+1]) need at most krows[g] rows
   uint32_t* tk_cmax;              // top-k: largest key per 32-column chunk of the scores [M, Bmax, n_chunks] (EpiScoresTma)
   int topk_cmax;                  // 1: the selection works from the chunk maxima (SCE_TOPK_CMAX=0 turns it off)
   int *tk_col, *tk_cnt;           // top-k lists (TopkLists): selected columns [M, Bmax, kmax], entries per row [M, Bmax]
@@ -172,9 +175,9 @@ static size_t topk_kmax(const sce_desc& d) {
 // count a plan uses: the smallest of 2, 4, 8 whose slice fits (two blocks per SM); 0 when none does (the plan then runs
 // the dense GEMMs)
 constexpr int kTopkMaxSlices = 8;
-static size_t topk_sparse_smem(const sce_desc& d, size_t kmax, int slices) {
+static size_t topk_sparse_smem(const sce_desc& d, size_t krows, int slices) {
   const size_t ds = d.d / slices;
-  return kmax * ds * sizeof(float) + 9 * ds * sizeof(float) + kmax * 8 + 128;
+  return krows * ds * sizeof(float) + 9 * ds * sizeof(float) + krows * 8 + 128;
 }
 static int topk_slices(const sce_desc& d, size_t kmax) {
   int best = 0;
@@ -235,7 +238,7 @@ static size_t carve(sce_plan* p, const sce_desc& d, uint8_t* base) {
   // top-k: scores of their own (the code-gradient planes must keep their scattered zeros) and the k-sparse lists
   const size_t kmax = topk_kmax(d);
   float* sc = nullptr;
-  int *tkc = nullptr, *tkn = nullptr;
+  int *tkc = nullptr, *tkn = nullptr, *tkm = nullptr;
   float *tkv = nullptr, *tkd = nullptr, *wnf = nullptr;
   uint32_t* tcm = nullptr;
   if (d.variant == SCE_TOPK) {
@@ -245,6 +248,7 @@ static size_t carve(sce_plan* p, const sce_desc& d, uint8_t* base) {
       tkc = c.take<int>(M * B * kmax);
       tkv = c.take<float>(M * B * kmax);
       tkn = c.take<int>(M * B);
+      tkm = c.take<int>(M);
       tkd = c.take<float>(M * B * kmax * kTopkMaxSlices);
       wnf = c.take<float>(M * n * dd);
     }
@@ -293,6 +297,7 @@ static size_t carve(sce_plan* p, const sce_desc& d, uint8_t* base) {
     p->x_centered = xcen;
     p->scores = sc;
     p->tk_cmax = tcm;
+    p->tk_models = tkm;
     p->tk_col = tkc;
     p->tk_val = tkv;
     p->tk_cnt = tkn;
@@ -755,10 +760,16 @@ static int run_pipeline_t(sce_plan* p, const float* x, int B, float* x_hat, bool
   if (sparse) {
     // ---- k-sparse decode + residual + loss partial + g planes + the code gradient at the selected entries
     const float gscale = f8 ? 1.0f : 2.0f / ((float)B * (float)dd);
-    topk_sparse_kernel<AR><<<dim3(B, M, p->tk_slices), 256, topk_sparse_smem(d, p->tk_kmax, p->tk_slices), st>>>(
-        tk, p->b.sparsity, p->wn_f32, x, d.x_per_model ? (long long)B * dd : 0, p->g_hi, p->g_lo, p->g_x8, x_hat, p->part_dec,
-        backward ? p->tk_dots : nullptr, B, n, dd, gscale);
-    ++launches;
+    // one launch per k class (sce_prepare sorted the models): a block's shared memory goes with ITS models' k, so the
+    // k = 16 and k = 32 models of a mixed ensemble run at 5 and 3 blocks per SM instead of the 2 that k_max = 64 allows
+    for (int g = 0; g < p->tk_groups; ++g) {
+      const int cnt = p->tk_group_off[g + 1] - p->tk_group_off[g];
+      if (cnt == 0) continue;
+      topk_sparse_kernel<AR><<<dim3(B, cnt, p->tk_slices), 256, topk_sparse_smem(d, p->tk_group_krows[g], p->tk_slices), st>>>(
+          tk, p->b.sparsity, p->wn_f32, x, d.x_per_model ? (long long)B * dd : 0, p->g_hi, p->g_lo, p->g_x8, x_hat, p->part_dec,
+          backward ? p->tk_dots : nullptr, B, n, dd, gscale, p->tk_models + p->tk_group_off[g], p->tk_group_krows[g]);
+      ++launches;
+    }
     CUDA_TRY(cudaGetLastError());
     n_dec_parts = p->tk_slices * B;
   } else {
@@ -961,10 +972,13 @@ int sce_plan_create(const sce_desc* desc, const sce_buffers* buffers, sce_plan**
         p->tk_slices = sl;
     }
     // Worth it where the dictionary is large against k: the dense decode + dcode GEMMs cost ~ n per row, the gather
-    // kernel ~ k (it is bound by the latency chain of a block, not by bytes). Measured on B200 (profiles/r02d_topk_*):
-    // d = 768, 12 models, k in {16, 32, 64}: n = 6144 dense 2.9 ms / sparse 3.7 ms, n = 12288 dense 5.8 ms / sparse 3.7 ms.
+    // kernel ~ k (it is bound by the latency chain of a block, not by bytes). Measured on B200, d = 768, 12 models,
+    // k in {16, 32, 64}, one launch per k class (tools/run_r02w.sh): n = 6144 dense 1.40 + 1.50 ms / sparse 2.56 + 0.31 ms —
+    // equal as kernels, but the step with the gather path is 4 % shorter (7.83 against 8.17 ms: the GPU runs these steps
+    // at its power cap and the gather kernel leaves the tensor pipes idle); n = 12288 dense 5.8 ms / sparse 2.9 ms;
+    // n = 3072: config 3 with every group on the gather path 22.26 ms against an estimated 22.15 ms with this rule.
     // SCE_TOPK_SPARSE = 1 / 0 forces it on / off.
-    const int heuristic = (long long)desc->n >= 160ll * (long long)(kmax ? kmax : 1);
+    const int heuristic = (long long)desc->n >= 96ll * (long long)(kmax ? kmax : 1);
     p->topk_sparse = desc->variant == SCE_TOPK && kmax > 0 && p->tk_slices > 0 && tune_flag("SCE_TOPK_SPARSE", heuristic);
     // selection from the per-chunk maxima the scores epilogue writes (profiles/r02p_*); 0 = read every row twice as before
     p->topk_cmax = desc->variant == SCE_TOPK && tune_flag("SCE_TOPK_CMAX", 1);
@@ -1008,6 +1022,30 @@ int sce_prepare(sce_plan* p, void* stream) {
     CUDA_TRY(cudaMemsetAsync(p->dz_hi, 0, el * 4, st));   // (the code-gradient planes are one contiguous block, 4 B / element)
     CUDA_TRY(cudaMemsetAsync(p->act_pos, 0, (size_t)d.n_models * ((d.n + 31) / 32) * d.batch_max * sizeof(uint32_t), st));
     CUDA_TRY(cudaMemsetAsync(p->tk_cnt, 0, (size_t)d.n_models * d.batch_max * sizeof(int), st));
+    // k classes for the gather kernel: rows of shared memory in {8, 16, 32, 64, ...} capped at the list capacity
+    std::vector<long long> ks(d.n_models);
+    CUDA_TRY(cudaMemcpyAsync(ks.data(), p->b.sparsity, ks.size() * sizeof(long long), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    const int caps[4] = {16, 32, 64, p->tk_kmax};
+    std::vector<int> order;
+    p->tk_groups = 0;
+    p->tk_group_off[0] = 0;
+    int lo = 0;
+    for (int g = 0; g < 4; ++g) {
+      const int cap = caps[g] < p->tk_kmax ? caps[g] : p->tk_kmax;
+      if (g > 0 && cap <= lo) continue;
+      for (int m = 0; m < d.n_models; ++m) {
+        const long long k = ks[m] < 1 ? 1 : (ks[m] > p->tk_kmax ? (long long)p->tk_kmax : ks[m]);   // (kernels clip k the same way)
+        if (k > lo && k <= cap) order.push_back(m);
+      }
+      p->tk_group_krows[p->tk_groups] = cap;
+      p->tk_group_off[++p->tk_groups] = (int)order.size();
+      lo = cap;
+      if (cap == p->tk_kmax) break;
+    }
+    if ((int)order.size() != d.n_models) return fail(SCE_ERR_INVALID, "top-k classes: %d of %d models placed", (int)order.size(), d.n_models);
+    CUDA_TRY(cudaMemcpyAsync(p->tk_models, order.data(), order.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaStreamSynchronize(st));   // (`order` is a local)
   }
   if (d.centering) {
     if (!p->b.center_trans || !p->b.center_rot || !p->b.center_scale)

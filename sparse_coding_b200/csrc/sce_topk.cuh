@@ -435,20 +435,23 @@ __global__ void __launch_bounds__(256) topk_sparse_kernel(TopkLists lists, const
                                                           void* __restrict__ g_x8, float* __restrict__ x_hat,
                                                           float* __restrict__ part /*[M][B][slices]*/,
                                                           float* __restrict__ dots /*[M][batch_max][kmax][slices]*/,
-                                                          int B, int n, int d, float gscale) {
+                                                          int B, int n, int d, float gscale,
+                                                          const int* __restrict__ models /*this launch's models or nullptr*/,
+                                                          int krows /*shared-memory rows: >= the k of every model of the launch*/) {
   extern __shared__ __align__(128) uint8_t smem_b[];
   __shared__ float red[8];
-  const int row = blockIdx.x, model = blockIdx.y, slice = blockIdx.z, slices = gridDim.z;
+  // (a launch covers the models of one k class, so that its blocks take k x slice bytes of shared memory, not k_max x)
+  const int row = blockIdx.x, model = models ? __ldg(models + blockIdx.y) : (int)blockIdx.y, slice = blockIdx.z, slices = gridDim.z;
   const int ds = d / slices, groups = ds >> 2;   // this block's columns, float4 groups of them
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int kmax = lists.kmax;
-  float* s_w = reinterpret_cast<float*>(smem_b);            // [kmax][ds]
-  float* s_part = s_w + (size_t)kmax * ds;                   // [8][ds]
+  float* s_w = reinterpret_cast<float*>(smem_b);            // [krows][ds]
+  float* s_part = s_w + (size_t)krows * ds;                  // [8][ds]
   float* s_g = s_part + 8 * ds;                              // [ds]
-  float* s_val = s_g + ds;                                   // [kmax]
+  float* s_val = s_g + ds;                                   // [krows]
   const long long lrow = (long long)model * lists.batch_max + row;
   // entries of the row = min(k, n, kmax), as the selection wrote them (no dependent load of lists.cnt)
-  int cnt = (int)min((long long)min(n, kmax), __ldg(sparsity + model));
+  int cnt = (int)min((long long)min(min(n, kmax), krows), __ldg(sparsity + model));
   // ---- gather: entry j, 16-byte piece q of its slice; every thread reads the column of its entry itself (one
   // dependent global load before the copies are in flight, not two), values and the x row are fetched alongside
   // (warp per entry: ONE column load and one base address per dictionary row, lanes stride its 16-byte pieces — the first
