@@ -105,6 +105,7 @@ struct sce_plan {
   int pair_encode, pair_decode, pair_dcode, pair_dw;  // 1: run that GEMM on CTA pairs (cta_group::2, 256-row tiles)
   int bk_encode, bk_decode, bk_dcode;  // K block (64: 128-byte swizzle, 32: 64-byte swizzle) of the K-major GEMMs
   int dw_collector;  // NSUB = 2 tiles: A slice kept in the tensor core's collector across the two column halves (SCE_TUNE_DW_COLL)
+  int dec_nsub2;     // experiment: decode with 256 x 512 tiles (SCE_TUNE_DEC_NSUB2)
   int dw_nsub2;      // f16f8 weight gradient: 256 x 512 tiles sharing one A tile (env SCE_TUNE_DW_NSUB2 = 0 switches it off)
   int last_launches;
   long long step;  // number of optimiser steps taken
@@ -788,7 +789,13 @@ static int run_pipeline_t(sce_plan* p, const float* x, int B, float* x_hat, bool
   dp.tiles_m = tiles_mB;
   dp.gscale = f8 ? 1.0f : 2.0f / ((float)B * (float)dd);
   dp.tiles_n = dd > 128 ? (dd + 255) / 256 : 1;
-  if (p->split_decode && !f8)
+  if (f8 && p->dec_nsub2 && dd % 512 == 0 && pair_ok(p->pair_decode, B, dd)) {
+    // experiment (SCE_TUNE_DEC_NSUB2=1): 256 x 512 tiles — the code tile (A) read once for both column halves, kept in the
+    // collector; the accumulators fill all of tensor memory, so the epilogue no longer overlaps the next main loop
+    if constexpr (f8)
+      rc = launch_gemm_t<EpiDec, 256, kBkF8, false, true, 4, false, true, kArithF16F8, 2>(p, maps->decode, 1, one, one, n, d.fwd_passes,
+                                                                                      B, dd, dp, st);
+  } else if (p->split_decode && !f8)
     rc = launch_k<EpiDec, true, true, AR>(dd > 128, p->bk_decode, pair_ok(p->pair_decode, B, dd), p, maps->decode, 1, one, one,
                                           n, d.fwd_passes, B, dd, dp, st);
   else
@@ -957,6 +964,7 @@ int sce_plan_create(const sce_desc* desc, const sce_buffers* buffers, sce_plan**
   // kernel is bound by the power-limited tensor rate either way) — off by default, kept as a knob
   p->dw_nsub2 = tune_flag("SCE_TUNE_DW_NSUB2", 1);
   p->dw_collector = tune_flag("SCE_TUNE_DW_COLL", 1);
+  p->dec_nsub2 = tune_flag("SCE_TUNE_DEC_NSUB2", 0);
   p->bk_encode = tune_bk("SCE_TUNE_BK_ENCODE", 64);
   p->bk_decode = tune_bk("SCE_TUNE_BK_DECODE", 32);
   p->bk_dcode = tune_bk("SCE_TUNE_BK_DCODE", 64);
